@@ -1,0 +1,167 @@
+/*
+ * mtraffic.h -- C ABI of libmtraffic, the B200 (sm_100a) engine for the
+ * batched finite-volume step of the macroscopic traffic models.
+ *
+ * Drop-in boundary.  The reference exposes the step as Python methods of
+ * its Model classes; each entry point below names the reference interface it
+ * replaces (paths relative to the reference checkout):
+ *
+ *   mt_create / mt_destroy   <- Model.__init__            mbrl_traffic/models/base.py:26-48
+ *                               LWRModel.__init__         mbrl_traffic/models/lwr.py:56-186
+ *                               ARZModel.__init__         mbrl_traffic/models/arz.py:60-199
+ *   mt_set_params            <- the attribute writes the reference performs
+ *                               between steps: fitness_fn lwr.py:161-164,
+ *                               arz.py:169-173; update() lwr.py:322-325,
+ *                               arz.py:498-502; load() lwr.py:371-379,
+ *                               arz.py:549-558
+ *   mt_step                  <- Model.get_next_obs(obs, action)
+ *                               base.py:58-74, lwr.py:192-204, arz.py:205-221
+ *   mt_rollout               <- the chained-step loop of
+ *                               experiments/evaluate_model.py:398-403 and the
+ *                               K-shoot rollout shape policies/kshoot.py:65-85
+ *   mt_step_host             <- the same get_next_obs call on host (NumPy)
+ *                               buffers, copies included
+ *   mt_density_sqerr         <- Model.compute_loss(...)   lwr.py:329-343,
+ *                               arz.py:506-520 (per-row squared density error;
+ *                               the caller takes the mean)
+ *
+ * All pointers are plain addresses, sizes are plain integers; there are no
+ * torch or CUDA types in the signatures (a stream is passed as `void*`
+ * holding a cudaStream_t, NULL = the legacy default stream).
+ *
+ * Data layout.  An observation batch is a dense row-major (n_envs, 2*n_cells)
+ * array of the engine dtype; row b is [rho_0..rho_{N-1} | v_0..v_{N-1}],
+ * exactly the reference's per-env observation (lwr.py:197,204;
+ * arz.py:210-211,221).  Input and output batches must not overlap.
+ *
+ * Every function returns MT_OK (0) or a negative mt_status; the message of
+ * the last failure on the calling thread is returned by mt_last_error().
+ * There is no CPU fallback: without a CUDA device every compute entry point
+ * fails with MT_ECUDA.
+ */
+#ifndef MTRAFFIC_H_
+#define MTRAFFIC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MT_VERSION 100 /* 0.1.0 */
+
+typedef struct mt_engine mt_engine;
+
+typedef enum mt_status {
+  MT_OK = 0,
+  MT_EINVAL = -1,  /* bad argument (unknown model/bc/dtype, bad shape, NULL) */
+  MT_ECUDA = -2,   /* CUDA runtime error or no device                        */
+  MT_ENOMEM = -3,  /* host or device allocation failed                       */
+  MT_ESTATE = -4   /* call order violated (e.g. step before set_params)      */
+} mt_status;
+
+typedef enum mt_model {
+  MT_MODEL_LWR = 0,      /* lwr.py  */
+  MT_MODEL_ARZ = 1,      /* arz.py  */
+  MT_MODEL_NONLOCAL = 2  /* paper cited at lwr.py:209-211; no reference code */
+} mt_model;
+
+typedef enum mt_dtype { MT_F32 = 0, MT_F64 = 1 } mt_dtype;
+
+/* Boundary rule of one road end.  The reference's three modes
+ * (lwr.py:237-264, arz.py:316-364) are LOOP/LOOP, EXTEND/EXTEND and
+ * CONSTANT/CONSTANT; mixed ends (e.g. CONSTANT inflow + EXTEND outflow) and
+ * HALO (the cell is a ghost owned by a neighbouring rank and is left as is)
+ * are additions used by the highway and domain-decomposed configurations. */
+typedef enum mt_bc {
+  MT_BC_LOOP = 0,
+  MT_BC_EXTEND = 1,
+  MT_BC_CONSTANT = 2,
+  MT_BC_HALO = 3
+} mt_bc;
+
+enum {
+  /* mt_params.flags */
+  MT_FLAG_FAST_MATH = 1 /* allow FMA contraction and approximate division
+                           (not bit-comparable; f32 throughput mode)       */
+};
+
+/* Fixed for the life of an engine. */
+typedef struct mt_config {
+  int32_t model;        /* mt_model                                          */
+  int32_t dtype;        /* mt_dtype                                          */
+  int64_t n_envs;       /* B: independent roads in the batch                 */
+  int64_t n_cells;      /* N: cells per road (observation row = 2N values)   */
+  int32_t device;       /* CUDA device ordinal                               */
+  int32_t max_n_eta;    /* non-local: largest look-ahead window in cells     */
+  int32_t host_staging; /* !=0: allocate device staging for mt_step_host     */
+  int32_t reserved;
+} mt_config;
+
+/* Model parameters; the names follow the reference attributes
+ * (lwr.py:128-138, arz.py:134-145, arz.py:199).  A per-env pointer, when not
+ * NULL, is a DEVICE array of n_envs values of the engine dtype and overrides
+ * the scalar of the same name. */
+typedef struct mt_params {
+  double dx, dt;
+  double rho_max, v_max, tau, lam;
+  double rho_crit;            /* ARZ: frozen at construction (arz.py:199);
+                                 <0 means rho_max/2.  Ignored by LWR, which
+                                 recomputes rho_max/2 every call (lwr.py:282) */
+  const void *rho_max_env, *v_max_env, *tau_env, *lam_env, *rho_crit_env;
+  int32_t bc_left, bc_right;  /* mt_bc                                       */
+  double bc_left_val[2];      /* CONSTANT: rho (LWR, non-local) or (rho, y)  */
+  double bc_right_val[2];     /*           for ARZ (arz.py:347-360)          */
+  const void *gamma;          /* non-local: DEVICE array of n_eta weights    */
+  int32_t n_eta;
+  int32_t flags;
+} mt_params;
+
+int mt_version(void);
+const char *mt_last_error(void);
+
+int mt_create(const mt_config *cfg, mt_engine **out);
+void mt_destroy(mt_engine *e);
+
+/* Derive the per-env constant table on the device (asynchronous on stream). */
+int mt_set_params(mt_engine *e, const mt_params *p, void *stream);
+
+/* One step for the whole batch.  obs_in/obs_out: DEVICE (B, 2N).  action:
+ * DEVICE [B] speed limits overriding v_max for this step, or NULL (the
+ * reference discards the action, lwr.py:194, arz.py:207).  reward_out: DEVICE
+ * [B] density-weighted mean speed of the new state, or NULL.  Asynchronous;
+ * no allocation; no host synchronisation. */
+int mt_step(mt_engine *e, const void *obs_in, const void *action,
+            void *obs_out, void *reward_out, void *stream);
+
+/* n_steps chained steps ping-ponging between two caller-owned DEVICE batches,
+ * starting from obs_a.  actions: DEVICE [n_steps, B] or NULL.  rewards:
+ * DEVICE [n_steps, B] or NULL.  *result_in_b is set to 1 when the final state
+ * is in obs_b, else 0. */
+int mt_rollout(mt_engine *e, void *obs_a, void *obs_b, const void *actions,
+               void *rewards, int32_t n_steps, void *stream,
+               int32_t *result_in_b);
+
+/* get_next_obs on HOST buffers (pinned for full speed): copies obs (and the
+ * action) to the device, runs n_steps chained steps, copies the final
+ * observation (and the last step's rewards) back and synchronises.  Needs
+ * cfg.host_staging. */
+int mt_step_host(mt_engine *e, const void *obs_in_host,
+                 const void *action_host, void *obs_out_host,
+                 void *reward_out_host, int32_t n_steps);
+
+/* out[b] = sum over the density half of (pred - target)^2, DEVICE pointers. */
+int mt_density_sqerr(mt_engine *e, const void *obs_pred,
+                     const void *obs_target, void *out_per_env, void *stream);
+
+/* Number of kernels this engine has launched so far. */
+int mt_launch_count(const mt_engine *e, int64_t *out);
+
+/* Page-locked host memory for mt_step_host callers. */
+int mt_alloc_pinned(uint64_t bytes, void **out);
+int mt_free_pinned(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTRAFFIC_H_ */

@@ -1,0 +1,217 @@
+"""Shared host logic of the finite-volume models (LWR / ARZ / non-local).
+
+The subclasses only declare their constructor (the reference signatures) and
+which attributes feed the engine.  Everything numerical happens in
+``libmtraffic.so``; this module converts observations, caches one engine per
+``(batch, cells, dtype)`` and re-derives the device parameter table whenever
+a model attribute changed since the last call -- the reference mutates
+attributes between steps (fitness_fn lwr.py:161-164, arz.py:169-173; load();
+the tests at tests/fast_tests/test_models.py:100-162 assign them directly).
+"""
+import numpy as np
+
+from mbrl_traffic_b200.base import Model
+from mbrl_traffic_b200.engine import Engine, dtype_name
+
+
+def _is_torch(x):
+    return hasattr(x, "data_ptr") and hasattr(x, "device")
+
+
+class FiniteVolumeModel(Model):
+    """Common machinery; see ``LWRModel`` / ``ARZModel`` / ``NonLocalModel``."""
+
+    #: engine model name, set by subclasses
+    _engine_model = None
+    #: attributes that may be scalars or per-env arrays
+    _param_names = ("rho_max", "v_max", "lam")
+
+    def __init__(self, sess, ob_space, ac_space, replay_buffer, verbose,
+                 device=0, action_is_speed_limit=False, fast_math=False):
+        super(FiniteVolumeModel, self).__init__(
+            sess=sess, ob_space=ob_space, ac_space=ac_space,
+            replay_buffer=replay_buffer, verbose=verbose)
+        #: CUDA device ordinal of the engine
+        self.device = device
+        #: if True, ``action`` (one value per env) overrides ``v_max`` for the
+        #: step -- the use the reference documents (lwr.py:98-101) but never
+        #: implemented (it deletes the action, lwr.py:194, arz.py:207)
+        self.action_is_speed_limit = action_is_speed_limit
+        #: allow FMA contraction / approximate division (not bit-comparable)
+        self.fast_math = fast_math
+        self._engines = {}
+        self._param_keys = {}
+
+    # ------------------------------------------------------------------ #
+    # reference-compatible no-ops                                        #
+    # ------------------------------------------------------------------ #
+    def initialize(self):
+        """See parent class (lwr.py:188-190, arz.py:201-203)."""
+        pass
+
+    def get_td_map(self):
+        """See parent class (lwr.py:345-347, arz.py:522-524)."""
+        return {}
+
+    # ------------------------------------------------------------------ #
+    # engine plumbing                                                    #
+    # ------------------------------------------------------------------ #
+    def _max_n_eta(self):
+        return 0
+
+    def _engine_kwargs(self):
+        """Extra ``Engine.set_params`` keywords (tau, rho_crit, gamma...)."""
+        return {}
+
+    def _get_engine(self, n_envs, n_cells, dtype, host):
+        key = (int(n_envs), int(n_cells), dtype, self.device, bool(host))
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = Engine(self._engine_model, dtype, n_envs, n_cells,
+                         device=self.device, max_n_eta=self._max_n_eta(),
+                         host_staging=host)
+            self._engines[key] = eng
+        self._sync_params(key, eng)
+        return eng
+
+    def _snapshot(self, value):
+        """Hashable identity of a parameter value for change detection."""
+        if _is_torch(value):
+            return ("t", value.data_ptr(), value._version, tuple(value.shape))
+        if isinstance(value, np.ndarray):
+            return ("a", value.tobytes(), value.shape)
+        if isinstance(value, (dict, list, tuple)):
+            return ("r", repr(value))
+        return ("s", value)
+
+    def _param_values(self):
+        d = dict(dx=self.dx, dt=self.dt,
+                 boundary_conditions=self.boundary_conditions)
+        for name in self._param_names:
+            d[name] = getattr(self, name)
+        d.update(self._engine_kwargs())
+        return d
+
+    def _sync_params(self, key, eng):
+        values = self._param_values()
+        snap = tuple((k, self._snapshot(v)) for k, v in sorted(values.items()))
+        snap += (("fast", self.fast_math),)
+        if self._param_keys.get(key) == snap:
+            return
+        kw = {}
+        for name, value in values.items():
+            if isinstance(value, np.ndarray) and name != "gamma":
+                import torch
+                value = torch.as_tensor(
+                    np.ascontiguousarray(value, dtype=eng.dtype),
+                    device="cuda:%d" % self.device)
+            kw[name] = value
+        stream = None if any(_is_torch(v) for v in kw.values()) else 0
+        eng.set_params(fast_math=self.fast_math, stream=stream, **kw)
+        self._param_keys[key] = snap
+
+    # ------------------------------------------------------------------ #
+    # the operator                                                       #
+    # ------------------------------------------------------------------ #
+    def get_next_obs(self, obs, action):
+        """Advance a batch of roads by one step.
+
+        Same contract as the reference (base.py:58-74): ``obs`` is
+        ``(2N,)`` or ``(batch, 2N)`` laid out ``[rho | v]`` per row; a new
+        array of the same shape/type is returned and ``obs`` is not modified.
+        ``action`` is discarded unless ``action_is_speed_limit`` is set.
+        NumPy in -> NumPy out (host path, copies included); torch CUDA tensor
+        in -> torch CUDA tensor out (device path, asynchronous).
+        """
+        return self.run(obs, action, n_steps=1)
+
+    def run(self, obs, action=None, n_steps=1, reward_out=None):
+        """``n_steps`` chained ``get_next_obs`` calls in one library call
+        (the loop of experiments/evaluate_model.py:398-403)."""
+        if not self.action_is_speed_limit:
+            action = None
+        if _is_torch(obs):
+            return self._run_device(obs, action, n_steps, reward_out)
+        return self._run_host(obs, action, n_steps, reward_out)
+
+    def _run_host(self, obs, action, n_steps, reward_out):
+        arr = np.asarray(obs)
+        if arr.dtype not in (np.float32, np.float64):
+            arr = arr.astype(np.float64)
+        squeeze = arr.ndim == 1
+        batch = np.ascontiguousarray(arr[None, :] if squeeze else arr)
+        if batch.ndim != 2 or batch.shape[1] % 2:
+            raise ValueError("obs must be (2N,) or (batch, 2N)")
+        n_envs, n_cells = batch.shape[0], batch.shape[1] // 2
+        eng = self._get_engine(n_envs, n_cells, batch.dtype.name, host=True)
+        out = np.empty_like(batch)
+        act = None
+        if action is not None:
+            act = np.ascontiguousarray(
+                np.asarray(action, dtype=batch.dtype).reshape(n_envs))
+        eng.step_host(batch, out, action=act, reward=reward_out,
+                      n_steps=n_steps)
+        return out[0] if squeeze else out
+
+    def _run_device(self, obs, action, n_steps, reward_out):
+        import torch
+        squeeze = obs.dim() == 1
+        batch = obs.unsqueeze(0) if squeeze else obs
+        batch = batch.contiguous()
+        if batch.dim() != 2 or batch.shape[1] % 2:
+            raise ValueError("obs must be (2N,) or (batch, 2N)")
+        n_envs, n_cells = batch.shape[0], batch.shape[1] // 2
+        eng = self._get_engine(n_envs, n_cells, dtype_name(batch.dtype),
+                               host=False)
+        out = torch.empty_like(batch)
+        if action is not None:
+            action = action.to(batch.dtype).reshape(n_envs).contiguous()
+        if n_steps == 1:
+            eng.step(batch, out, action=action, reward=reward_out)
+        else:
+            work = batch.clone()
+            res = eng.rollout(work, out, n_steps, rewards=reward_out)
+            out = res
+        return out[0] if squeeze else out
+
+    # ------------------------------------------------------------------ #
+    # loss                                                               #
+    # ------------------------------------------------------------------ #
+    def compute_loss(self, states, actions, next_states):
+        """Density-half MSE between ``next_states`` and the model's
+        prediction (lwr.py:329-343, arz.py:506-520), one batched step instead
+        of the reference's per-row Python loop."""
+        import torch
+        dev = "cuda:%d" % self.device
+        if _is_torch(states):
+            s = states.contiguous()
+            t = next_states.to(s.dtype).contiguous()
+        else:
+            arr = np.asarray(states)
+            if arr.dtype not in (np.float32, np.float64):
+                arr = arr.astype(np.float64)
+            s = torch.as_tensor(np.ascontiguousarray(arr), device=dev)
+            t = torch.as_tensor(
+                np.ascontiguousarray(np.asarray(next_states, dtype=arr.dtype)),
+                device=dev)
+        act = None
+        if self.action_is_speed_limit and actions is not None:
+            act = torch.as_tensor(np.asarray(actions), device=dev) \
+                if not _is_torch(actions) else actions
+            act = act.to(s.dtype).reshape(s.shape[0]).contiguous()
+        n_envs, n_cells = s.shape[0], s.shape[1] // 2
+        eng = self._get_engine(n_envs, n_cells, dtype_name(s.dtype),
+                               host=False)
+        pred = torch.empty_like(s)
+        eng.step(s, pred, action=act)
+        sq = torch.empty(n_envs, dtype=s.dtype, device=s.device)
+        eng.density_sqerr(pred, t, sq)
+        return float(sq.sum().item() / (n_envs * n_cells))
+
+    # ------------------------------------------------------------------ #
+    def close(self):
+        """Release the engines (device memory)."""
+        for eng in self._engines.values():
+            eng.close()
+        self._engines = {}
+        self._param_keys = {}

@@ -1,0 +1,926 @@
+// mtraffic.cu -- kernels and C ABI of libmtraffic (sm_100a).
+//
+// One fused kernel per model step: each thread owns one 16-byte vector of
+// consecutive cells (2 x f64 or 4 x f32) of one road, loads rho and v with one
+// coalesced 128-bit load each, derives the per-cell flux ingredients, swaps
+// the three edge values its neighbours need through shared memory (one
+// __syncthreads), applies the finite-volume update, the boundary rule and the
+// (rho, y) -> (rho, v) conversion, and stores one 128-bit vector per field.
+// Rewards are reduced per road with warp shuffles in the same kernel.
+//
+// Reference semantics reproduced here are cited function by function in
+// mt_math.cuh and below; the C ABI is documented in include/mtraffic.h.
+#include "mtraffic.h"
+#include "mt_math.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+namespace {
+
+using namespace mt;
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                        \
+  do {                                                                        \
+    cudaError_t _e = (expr);                                                  \
+    if (_e != cudaSuccess)                                                    \
+      return fail(MT_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));  \
+  } while (0)
+
+constexpr int MAX_BLOCK = 512;
+
+// ---------------------------------------------------------------------------
+// kernel arguments
+// ---------------------------------------------------------------------------
+template <typename T> struct StepArgs {
+  const T* in;
+  T* out;
+  const T* table;
+  const int* flags;
+  const T* action;    // [B] or nullptr
+  T* reward;          // [B] or nullptr
+  T* partial;         // [B, tiles, 2] scratch when tiles > 1
+  long long B;
+  int N;
+  int nvec;           // N / V (vector kernels)
+  int tpe;            // threads per env (padded) when tiles == 1
+  int epc;            // envs per CTA when tiles == 1
+  int tiles;          // CTAs per env
+  int bc_l, bc_r;
+  T step;
+  T bl0, bl1, br0, br1;  // CONSTANT boundary values
+};
+
+// thread -> (env, vector) mapping shared by the vector kernels
+struct Where {
+  long long env;
+  int vec;
+  int tile;
+  bool active;
+  bool tile_first;  // first thread of a tile of a multi-tile row
+  bool tile_last;
+};
+
+template <typename T>
+__device__ __forceinline__ Where locate(const StepArgs<T>& a) {
+  Where w;
+  const int t = threadIdx.x;
+  if (a.tiles == 1) {
+    const int el = t / a.tpe;
+    w.vec = t - el * a.tpe;
+    w.env = (long long)blockIdx.x * a.epc + el;
+    w.tile = 0;
+    w.active = (el < a.epc) && (w.env < a.B) && (w.vec < a.nvec);
+    w.tile_first = false;
+    w.tile_last = false;
+  } else {
+    w.env = blockIdx.x / a.tiles;
+    w.tile = blockIdx.x - (int)(w.env * a.tiles);
+    w.vec = w.tile * blockDim.x + t;
+    w.active = w.vec < a.nvec;
+    w.tile_first = (t == 0);
+    w.tile_last = (t == (int)blockDim.x - 1);
+  }
+  return w;
+}
+
+// Per-road reward sum(rho v) / sum(rho), deterministic order.
+// tpe <= 32: segmented butterfly inside the warp.  Otherwise warp butterfly,
+// one partial per warp in shared memory, then the road's first thread adds
+// its warps in order.  Multi-tile rows write one partial per tile.
+template <typename T>
+__device__ __forceinline__ void reduce_reward(const StepArgs<T>& a, const Where& w,
+                                              T num, T den, T* s_num, T* s_den) {
+  const unsigned full = 0xffffffffu;
+  const int t = threadIdx.x;
+  if (a.tiles == 1 && a.tpe <= 32) {
+    for (int off = a.tpe >> 1; off > 0; off >>= 1) {
+      num += __shfl_xor_sync(full, num, off);
+      den += __shfl_xor_sync(full, den, off);
+    }
+    if (w.active && w.vec == 0) a.reward[w.env] = num / den;
+    return;
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    num += __shfl_xor_sync(full, num, off);
+    den += __shfl_xor_sync(full, den, off);
+  }
+  if ((t & 31) == 0) { s_num[t >> 5] = num; s_den[t >> 5] = den; }
+  __syncthreads();
+  if (a.tiles == 1) {
+    if (w.active && w.vec == 0) {
+      const int w0 = t >> 5, nw = a.tpe >> 5;
+      T n = s_num[w0], d = s_den[w0];
+      for (int i = 1; i < nw; ++i) { n += s_num[w0 + i]; d += s_den[w0 + i]; }
+      a.reward[w.env] = n / d;
+    }
+  } else if (t == 0) {
+    const int nw = blockDim.x >> 5;
+    T n = s_num[0], d = s_den[0];
+    for (int i = 1; i < nw; ++i) { n += s_num[i]; d += s_den[i]; }
+    T* p = a.partial + ((long long)w.env * a.tiles + w.tile) * 2;
+    p[0] = n;
+    p[1] = d;
+  }
+}
+
+// one warp per env: fixed-order sum of the per-tile partials
+template <typename T>
+__global__ void reward_finalize_kernel(const T* __restrict__ partial, T* __restrict__ reward,
+                                       long long B, int tiles) {
+  const long long env = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (env >= B) return;
+  const int lane = threadIdx.x & 31;
+  T n = 0, d = 0;
+  for (int i = lane; i < tiles; i += 32) {
+    n += partial[(env * tiles + i) * 2];
+    d += partial[(env * tiles + i) * 2 + 1];
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    n += __shfl_xor_sync(0xffffffffu, n, off);
+    d += __shfl_xor_sync(0xffffffffu, d, off);
+  }
+  if (lane == 0) reward[env] = n / d;
+}
+
+// ---------------------------------------------------------------------------
+// ARZ step, vector kernel  (ARZModel.get_next_obs, arz.py:205-221)
+// ---------------------------------------------------------------------------
+template <typename T, bool FAST, bool REWARD>
+__global__ void __launch_bounds__(MAX_BLOCK, 2)
+arz_step_vec_kernel(const StepArgs<T> a) {
+  constexpr int V = Vec<T>::N;
+  using VT = typename Vec<T>::type;
+  using A = Ar<T, FAST>;
+  __shared__ T sS[MAX_BLOCK], sD[MAX_BLOCK], sR[MAX_BLOCK];
+  __shared__ T s_num[MAX_BLOCK / 32], s_den[MAX_BLOCK / 32];
+
+  const int t = threadIdx.x;
+  const Where w = locate(a);
+  const int N = a.N;
+
+  EnvC<T> e;
+  T rho[V], v[V], y[V], r[V], D[V], S[V];
+  const T* row = nullptr;
+  if (w.active) {
+    load_env(e, a.table, a.flags, w.env, a.action, a.step);
+    e.qc = A::mul(e.rho_crit, A::mul(e.v_max, e.g_crit));
+    row = a.in + w.env * (2LL * N);
+    unpack(__ldg(reinterpret_cast<const VT*>(row) + w.vec), rho);
+    unpack(__ldg(reinterpret_cast<const VT*>(row + N) + w.vec), v);
+#pragma unroll
+    for (int k = 0; k < V; ++k) arz_cell<T, FAST>(e, rho[k], v[k], y[k], r[k], D[k], S[k]);
+    sS[t] = S[0];
+    sD[t] = D[V - 1];
+    sR[t] = r[V - 1];
+  }
+  __syncthreads();
+
+  T num = 0, den = 0;
+  if (w.active) {
+    const bool row_first = (w.vec == 0), row_last = (w.vec == a.nvec - 1);
+    // supply of the cell to the right of my last cell (arz.py:405: the last
+    // cell of the road pairs with its own supply)
+    T S_right;
+    if (row_last) {
+      S_right = S[V - 1];
+    } else if (w.tile_last) {
+      const int j = (w.vec + 1) * V;
+      T yy, rr, dd;
+      arz_cell<T, FAST>(e, __ldg(row + j), __ldg(row + N + j), yy, rr, dd, S_right);
+    } else {
+      S_right = sS[t + 1];
+    }
+    T Q[V], P[V];
+#pragma unroll
+    for (int k = 0; k < V - 1; ++k) Q[k] = npmin(D[k], S[k + 1]);  // arz.py:408
+    Q[V - 1] = npmin(D[V - 1], S_right);
+#pragma unroll
+    for (int k = 0; k < V; ++k) P[k] = A::mul(Q[k], r[k]);         // arz.py:411
+    // flux through my left face (arz.py:414-415: cell 0 reuses its own flux)
+    T Qm, Pm;
+    if (row_first) {
+      Qm = Q[0];
+      Pm = P[0];
+    } else {
+      T D_left, r_left;
+      if (w.tile_first) {
+        const int j = w.vec * V - 1;
+        T yy, ss;
+        arz_cell<T, FAST>(e, __ldg(row + j), __ldg(row + N + j), yy, r_left, D_left, ss);
+      } else {
+        D_left = sD[t - 1];
+        r_left = sR[t - 1];
+      }
+      Qm = npmin(D_left, S[0]);
+      Pm = A::mul(Qm, r_left);
+    }
+    T rn[V], yn[V], vn[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      arz_advance<T, FAST>(e, rho[k], y[k], Qm, Q[k], Pm, P[k], rn[k], yn[k]);
+      Qm = Q[k];
+      Pm = P[k];
+    }
+    // boundary cells (arz.py:316-360)
+    if (row_first) {
+      if (a.bc_l == MT_BC_LOOP) {            // old state of the last cell
+        const T rl = __ldg(row + N - 1), vl = __ldg(row + 2 * N - 1);
+        rn[0] = rl;
+        yn[0] = arz_y<T, FAST>(e, rl, vl);
+      } else if (a.bc_l == MT_BC_EXTEND) {   // new state of cell 1
+        rn[0] = rn[1];
+        yn[0] = yn[1];
+      } else if (a.bc_l == MT_BC_CONSTANT) {
+        rn[0] = a.bl0;
+        yn[0] = a.bl1;
+      } else {                               // HALO: ghost, left as is
+        rn[0] = rho[0];
+        yn[0] = y[0];
+      }
+    }
+    if (row_last) {
+      if (a.bc_r == MT_BC_LOOP) {            // old state of cell N-2
+        rn[V - 1] = rho[V - 2];
+        yn[V - 1] = y[V - 2];
+      } else if (a.bc_r == MT_BC_EXTEND) {   // new state of cell N-2
+        rn[V - 1] = rn[V - 2];
+        yn[V - 1] = yn[V - 2];
+      } else if (a.bc_r == MT_BC_CONSTANT) {
+        rn[V - 1] = a.br0;
+        yn[V - 1] = a.br1;
+      } else {
+        rn[V - 1] = rho[V - 1];
+        yn[V - 1] = y[V - 1];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      arz_u<T, FAST>(e, rn[k], yn[k], vn[k]);
+      if (REWARD) { num += rn[k] * vn[k]; den += rn[k]; }
+    }
+    T* orow = a.out + w.env * (2LL * N);
+    reinterpret_cast<VT*>(orow)[w.vec] = pack(rn);
+    reinterpret_cast<VT*>(orow + N)[w.vec] = pack(vn);
+  }
+  if (REWARD) reduce_reward(a, w, num, den, s_num, s_den);
+}
+
+// ---------------------------------------------------------------------------
+// LWR step, vector kernel  (LWRModel.get_next_obs, lwr.py:192-266)
+// ---------------------------------------------------------------------------
+template <typename T, bool FAST, bool REWARD>
+__global__ void __launch_bounds__(MAX_BLOCK)
+lwr_step_vec_kernel(const StepArgs<T> a) {
+  constexpr int V = Vec<T>::N;
+  using VT = typename Vec<T>::type;
+  __shared__ T sS[MAX_BLOCK], sD[MAX_BLOCK];
+  __shared__ T s_num[MAX_BLOCK / 32], s_den[MAX_BLOCK / 32];
+
+  const int t = threadIdx.x;
+  const Where w = locate(a);
+  const int N = a.N;
+
+  EnvC<T> e;
+  T rho[V], D[V], S[V];
+  const T* row = nullptr;
+  if (w.active) {
+    load_env(e, a.table, a.flags, w.env, a.action, a.step);
+    row = a.in + w.env * (2LL * N);   // the velocity half is ignored (lwr.py:197)
+    unpack(__ldg(reinterpret_cast<const VT*>(row) + w.vec), rho);
+#pragma unroll
+    for (int k = 0; k < V; ++k) lwr_cell<T, FAST>(e, rho[k], D[k], S[k]);
+    sS[t] = S[0];
+    sD[t] = D[V - 1];
+  }
+  __syncthreads();
+
+  T num = 0, den = 0;
+  if (w.active) {
+    const bool row_first = (w.vec == 0), row_last = (w.vec == a.nvec - 1);
+    T S_right;
+    if (row_last) {
+      S_right = S[V - 1];                               // lwr.py:294
+    } else if (w.tile_last) {
+      T dd;
+      lwr_cell<T, FAST>(e, __ldg(row + (w.vec + 1) * V), dd, S_right);
+    } else {
+      S_right = sS[t + 1];
+    }
+    T f[V];
+#pragma unroll
+    for (int k = 0; k < V - 1; ++k) f[k] = npmin(D[k], S[k + 1]);
+    f[V - 1] = npmin(D[V - 1], S_right);
+    T fm;
+    if (row_first) {
+      fm = f[0];                                        // lwr.py:231
+    } else {
+      T D_left;
+      if (w.tile_first) {
+        T ss;
+        lwr_cell<T, FAST>(e, __ldg(row + w.vec * V - 1), D_left, ss);
+      } else {
+        D_left = sD[t - 1];
+      }
+      fm = npmin(D_left, S[0]);
+    }
+    T rn[V], vn[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      rn[k] = lwr_advance<T, FAST>(e, rho[k], f[k], fm);
+      fm = f[k];
+    }
+    // boundary cells (lwr.py:237-260).  EXTEND keeps the scheme's own values.
+    const T keep_second_last = rn[V - 2];
+    if (row_first) {
+      if (a.bc_l == MT_BC_LOOP) {     // UPDATED value of the last cell
+        const T r2 = __ldg(row + N - 2), r1 = __ldg(row + N - 1);
+        T D2, S2, D1, S1;
+        lwr_cell<T, FAST>(e, r2, D2, S2);
+        lwr_cell<T, FAST>(e, r1, D1, S1);
+        rn[0] = lwr_advance<T, FAST>(e, r1, npmin(D1, S1), npmin(D2, S1));
+      } else if (a.bc_l == MT_BC_CONSTANT) {
+        rn[0] = a.bl0;
+      } else if (a.bc_l == MT_BC_HALO) {
+        rn[0] = rho[0];
+      }
+    }
+    if (row_last) {
+      if (a.bc_r == MT_BC_LOOP) {     // UPDATED value of cell N-2
+        rn[V - 1] = keep_second_last;
+      } else if (a.bc_r == MT_BC_CONSTANT) {
+        rn[V - 1] = a.br0;
+      } else if (a.bc_r == MT_BC_HALO) {
+        rn[V - 1] = rho[V - 1];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      vn[k] = v_eq<T, FAST>(rn[k], e);                  // lwr.py:201
+      if (REWARD) { num += rn[k] * vn[k]; den += rn[k]; }
+    }
+    T* orow = a.out + w.env * (2LL * N);
+    reinterpret_cast<VT*>(orow)[w.vec] = pack(rn);
+    reinterpret_cast<VT*>(orow + N)[w.vec] = pack(vn);
+  }
+  if (REWARD) reduce_reward(a, w, num, den, s_num, s_den);
+}
+
+// ---------------------------------------------------------------------------
+// scalar kernels: any N >= 3, one thread per cell, neighbours re-derived from
+// global memory.  Used when N is not a multiple of the vector width (or the
+// buffers are not 16-byte aligned) and as an independent cross-check of the
+// vector kernels in the tests.
+// ---------------------------------------------------------------------------
+template <typename T, bool FAST>
+__device__ __forceinline__ void arz_interior(const EnvC<T>& e, const T* __restrict__ row, int N,
+                                             int j, T& rho_n, T& y_n) {
+  using A = Ar<T, FAST>;
+  T yL, rL, DL, SL, yC, rC, DC, SC, yR, rR, DR, SR;
+  arz_cell<T, FAST>(e, __ldg(row + j - 1), __ldg(row + N + j - 1), yL, rL, DL, SL);
+  arz_cell<T, FAST>(e, __ldg(row + j), __ldg(row + N + j), yC, rC, DC, SC);
+  arz_cell<T, FAST>(e, __ldg(row + j + 1), __ldg(row + N + j + 1), yR, rR, DR, SR);
+  const T Q = npmin(DC, SR), Qm = npmin(DL, SC);
+  const T P = A::mul(Q, rC), Pm = A::mul(Qm, rL);
+  arz_advance<T, FAST>(e, __ldg(row + j), yC, Qm, Q, Pm, P, rho_n, y_n);
+}
+
+template <typename T, bool FAST>
+__global__ void arz_step_scalar_kernel(const StepArgs<T> a) {
+  using A = Ar<T, FAST>;
+  const int N = a.N;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= a.B * N) return;
+  const long long env = gid / N;
+  const int i = (int)(gid - env * N);
+  EnvC<T> e;
+  load_env(e, a.table, a.flags, env, a.action, a.step);
+  e.qc = A::mul(e.rho_crit, A::mul(e.v_max, e.g_crit));
+  const T* row = a.in + env * (2LL * N);
+  T rn, yn, vn;
+  if (i == 0) {
+    if (a.bc_l == MT_BC_LOOP) { rn = row[N - 1]; yn = arz_y<T, FAST>(e, rn, row[2 * N - 1]); }
+    else if (a.bc_l == MT_BC_EXTEND) arz_interior<T, FAST>(e, row, N, 1, rn, yn);
+    else if (a.bc_l == MT_BC_CONSTANT) { rn = a.bl0; yn = a.bl1; }
+    else { rn = row[0]; yn = arz_y<T, FAST>(e, rn, row[N]); }
+  } else if (i == N - 1) {
+    if (a.bc_r == MT_BC_LOOP) { rn = row[N - 2]; yn = arz_y<T, FAST>(e, rn, row[2 * N - 2]); }
+    else if (a.bc_r == MT_BC_EXTEND) arz_interior<T, FAST>(e, row, N, N - 2, rn, yn);
+    else if (a.bc_r == MT_BC_CONSTANT) { rn = a.br0; yn = a.br1; }
+    else { rn = row[N - 1]; yn = arz_y<T, FAST>(e, rn, row[2 * N - 1]); }
+  } else {
+    arz_interior<T, FAST>(e, row, N, i, rn, yn);
+  }
+  arz_u<T, FAST>(e, rn, yn, vn);
+  T* orow = a.out + env * (2LL * N);
+  orow[i] = rn;
+  orow[N + i] = vn;
+}
+
+// updated LWR density of cell j under the scheme alone (no boundary rule)
+template <typename T, bool FAST>
+__device__ __forceinline__ T lwr_scheme(const EnvC<T>& e, const T* __restrict__ row, int N, int j) {
+  T DC, SC, DL = 0, SL, DR, SR;
+  const T rc = __ldg(row + j);
+  lwr_cell<T, FAST>(e, rc, DC, SC);
+  if (j + 1 < N) lwr_cell<T, FAST>(e, __ldg(row + j + 1), DR, SR); else SR = SC;
+  const T f = npmin(DC, SR);
+  T fm = f;
+  if (j > 0) { lwr_cell<T, FAST>(e, __ldg(row + j - 1), DL, SL); fm = npmin(DL, SC); }
+  return lwr_advance<T, FAST>(e, rc, f, fm);
+}
+
+template <typename T, bool FAST>
+__global__ void lwr_step_scalar_kernel(const StepArgs<T> a) {
+  const int N = a.N;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= a.B * N) return;
+  const long long env = gid / N;
+  const int i = (int)(gid - env * N);
+  EnvC<T> e;
+  load_env(e, a.table, a.flags, env, a.action, a.step);
+  const T* row = a.in + env * (2LL * N);
+  T rn;
+  if (i == 0) {
+    if (a.bc_l == MT_BC_LOOP) rn = lwr_scheme<T, FAST>(e, row, N, N - 1);
+    else if (a.bc_l == MT_BC_EXTEND) rn = lwr_scheme<T, FAST>(e, row, N, 0);
+    else if (a.bc_l == MT_BC_CONSTANT) rn = a.bl0;
+    else rn = row[0];
+  } else if (i == N - 1) {
+    if (a.bc_r == MT_BC_LOOP) rn = lwr_scheme<T, FAST>(e, row, N, N - 2);
+    else if (a.bc_r == MT_BC_EXTEND) rn = lwr_scheme<T, FAST>(e, row, N, N - 1);
+    else if (a.bc_r == MT_BC_CONSTANT) rn = a.br0;
+    else rn = row[N - 1];
+  } else {
+    rn = lwr_scheme<T, FAST>(e, row, N, i);
+  }
+  T* orow = a.out + env * (2LL * N);
+  orow[i] = rn;
+  orow[N + i] = v_eq<T, FAST>(rn, e);
+}
+
+// reward for the scalar path: one warp per env over the finished output
+template <typename T>
+__global__ void reward_rows_kernel(const T* __restrict__ obs, T* __restrict__ reward,
+                                   long long B, int N) {
+  const long long env = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (env >= B) return;
+  const int lane = threadIdx.x & 31;
+  const T* row = obs + env * (2LL * N);
+  T n = 0, d = 0;
+  for (int i = lane; i < N; i += 32) { n += row[i] * row[N + i]; d += row[i]; }
+  for (int off = 16; off > 0; off >>= 1) {
+    n += __shfl_xor_sync(0xffffffffu, n, off);
+    d += __shfl_xor_sync(0xffffffffu, d, off);
+  }
+  if (lane == 0) reward[env] = n / d;
+}
+
+// ---------------------------------------------------------------------------
+// parameter table  (one thread per env)
+// ---------------------------------------------------------------------------
+template <typename T> struct ParamArgs {
+  T* table;
+  int* flags;
+  long long B;
+  int model;
+  double rho_max, v_max, tau, lam, rho_crit, dt;
+  const T *rho_max_env, *v_max_env, *tau_env, *lam_env, *rho_crit_env;
+};
+
+template <typename T> __device__ __forceinline__ bool is_pow2(T x) {
+  int ex;
+  return x > T(0) && frexp((double)x, &ex) == 0.5;
+}
+
+template <typename T>
+__global__ void set_params_kernel(const ParamArgs<T> p) {
+  const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= p.B) return;
+  using A = Ar<T, false>;
+  const T rho_max = p.rho_max_env ? p.rho_max_env[env] : (T)p.rho_max;
+  const T v_max = p.v_max_env ? p.v_max_env[env] : (T)p.v_max;
+  const T lam = p.lam_env ? p.lam_env[env] : (T)p.lam;
+  T rho_crit;
+  if (p.model == MT_MODEL_ARZ && p.rho_crit_env) rho_crit = p.rho_crit_env[env];
+  else if (p.model == MT_MODEL_ARZ && p.rho_crit >= 0) rho_crit = (T)p.rho_crit;
+  else rho_crit = A::div(rho_max, T(2));          // lwr.py:282, arz.py:199
+  // 1 + dt/tau  (arz.py:461, 492): double arithmetic for a scalar tau, as in
+  // the reference where both are Python floats.
+  T c;
+  if (p.tau_env) c = A::add(T(1), A::div((T)p.dt, p.tau_env[env]));
+  else c = (T)(1.0 + p.dt / p.tau);
+  int kind = LAM_GENERAL;
+  if (lam == T(1)) kind = LAM_ONE;
+  else if (lam == T(2)) kind = LAM_TWO;
+  else if (lam == T(0.5)) kind = LAM_HALF;
+  int fl = kind;
+  if (is_pow2(rho_max)) fl |= FLAG_RHO_MAX_POW2;
+  if (is_pow2(c)) fl |= FLAG_C_POW2;
+  // (1 - rho_crit/rho_max) ** lam  for q_max (arz.py:396)
+  const T base = A::sub(T(1), A::div(rho_crit, rho_max));
+  T g;
+  if (kind == LAM_ONE) g = base;
+  else if (kind == LAM_TWO) g = A::mul(base, base);
+  else if (kind == LAM_HALF) g = mt_sqrt(base);
+  else g = mt_pow(base, lam);
+  T* row = p.table + env * TBL_STRIDE;
+  row[TBL_RHO_MAX] = rho_max;
+  row[TBL_INV_RHO_MAX] = A::div(T(1), rho_max);
+  row[TBL_V_MAX] = v_max;
+  row[TBL_LAM] = lam;
+  row[TBL_RHO_CRIT] = rho_crit;
+  row[TBL_G_CRIT] = g;
+  row[TBL_C] = c;
+  row[TBL_INV_C] = A::div(T(1), c);
+  p.flags[env] = fl;
+}
+
+// ---------------------------------------------------------------------------
+// compute_loss support: per-env squared density error (lwr.py:338-343)
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void density_sqerr_kernel(const T* __restrict__ pred, const T* __restrict__ target,
+                                     T* __restrict__ out, long long B, int N) {
+  const long long env = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (env >= B) return;
+  const int lane = threadIdx.x & 31;
+  const T* p = pred + env * (2LL * N);
+  const T* q = target + env * (2LL * N);
+  T s = 0;
+  for (int i = lane; i < N; i += 32) { const T d = p[i] - q[i]; s += d * d; }
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) out[env] = s;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// engine
+// ---------------------------------------------------------------------------
+struct mt_engine {
+  mt_config cfg;
+  size_t elt;             // sizeof dtype
+  void* table = nullptr;  // [B, TBL_STRIDE]
+  int* flags = nullptr;   // [B]
+  void* partial = nullptr;
+  int max_tiles = 1;
+  bool have_params = false;
+  mt_params params;       // last set
+  int64_t launches = 0;
+  // table readiness: recorded by mt_set_params, awaited once by the next
+  // step issued on a different stream
+  cudaEvent_t params_ready = nullptr;
+  cudaStream_t params_stream = nullptr;
+  bool params_pending = false;
+  // host staging
+  cudaStream_t stream = nullptr;
+  void *d_a = nullptr, *d_b = nullptr, *d_action = nullptr, *d_reward = nullptr;
+};
+
+namespace {
+
+struct Geometry {
+  bool vector_ok;
+  int nvec, tpe, epc, tiles, block;
+  long long grid;
+};
+
+int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+Geometry plan(long long B, int N, int V, bool aligned) {
+  Geometry g;
+  g.vector_ok = aligned && (N % V == 0) && (N >= 2 * V);
+  g.nvec = N / V;
+  if (g.nvec <= MAX_BLOCK) {
+    g.tiles = 1;
+    g.tpe = g.nvec <= 32 ? next_pow2(g.nvec) : ((g.nvec + 31) / 32) * 32;
+    g.block = g.tpe <= 256 ? 256 : g.tpe;
+    g.epc = g.block / g.tpe;
+    g.grid = (B + g.epc - 1) / g.epc;
+  } else {
+    g.block = 256;
+    g.tpe = g.block;
+    g.epc = 1;
+    g.tiles = (g.nvec + g.block - 1) / g.block;
+    g.grid = B * (long long)g.tiles;
+  }
+  return g;
+}
+
+template <typename T>
+int step_typed(mt_engine* e, const void* obs_in, const void* action, void* obs_out,
+               void* reward_out, cudaStream_t stream) {
+  constexpr int V = Vec<T>::N;
+  const mt_params& p = e->params;
+  const long long B = e->cfg.n_envs;
+  const int N = (int)e->cfg.n_cells;
+  const bool aligned = (((uintptr_t)obs_in | (uintptr_t)obs_out) & 15u) == 0;
+  const Geometry g = plan(B, N, V, aligned);
+  const bool fast = (p.flags & MT_FLAG_FAST_MATH) != 0;
+
+  StepArgs<T> a;
+  a.in = (const T*)obs_in;
+  a.out = (T*)obs_out;
+  a.table = (const T*)e->table;
+  a.flags = e->flags;
+  a.action = (const T*)action;
+  a.reward = (T*)reward_out;
+  a.partial = (T*)e->partial;
+  a.B = B;
+  a.N = N;
+  a.nvec = g.nvec;
+  a.tpe = g.tpe;
+  a.epc = g.epc;
+  a.tiles = g.tiles;
+  a.bc_l = p.bc_left;
+  a.bc_r = p.bc_right;
+  a.step = (T)(p.dt / p.dx);
+  a.bl0 = (T)p.bc_left_val[0];
+  a.bl1 = (T)p.bc_left_val[1];
+  a.br0 = (T)p.bc_right_val[0];
+  a.br1 = (T)p.bc_right_val[1];
+
+  const bool rew = reward_out != nullptr;
+  if (g.grid > 0x7fffffffLL) return fail(MT_EINVAL, "batch too large for one launch");
+  if (g.vector_ok) {
+    const dim3 grid((unsigned)g.grid), block(g.block);
+#define MT_LAUNCH(KERNEL)                                                     \
+    do {                                                                      \
+      if (fast) { if (rew) KERNEL<T, true, true><<<grid, block, 0, stream>>>(a);  \
+                  else KERNEL<T, true, false><<<grid, block, 0, stream>>>(a); }   \
+      else { if (rew) KERNEL<T, false, true><<<grid, block, 0, stream>>>(a);      \
+             else KERNEL<T, false, false><<<grid, block, 0, stream>>>(a); }       \
+    } while (0)
+    if (e->cfg.model == MT_MODEL_ARZ) MT_LAUNCH(arz_step_vec_kernel);
+    else if (e->cfg.model == MT_MODEL_LWR) MT_LAUNCH(lwr_step_vec_kernel);
+    else return fail(MT_EINVAL, "model %d has no step kernel", e->cfg.model);
+#undef MT_LAUNCH
+    e->launches++;
+    if (rew && g.tiles > 1) {
+      const int wpb = 8;
+      reward_finalize_kernel<T><<<(unsigned)((B + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+          (const T*)e->partial, (T*)reward_out, B, g.tiles);
+      e->launches++;
+    }
+  } else {
+    const long long cells = B * (long long)N;
+    const int block = 256;
+    const long long grid = (cells + block - 1) / block;
+    if (grid > 0x7fffffffLL) return fail(MT_EINVAL, "batch too large for one launch");
+    if (e->cfg.model == MT_MODEL_ARZ) {
+      if (fast) arz_step_scalar_kernel<T, true><<<(unsigned)grid, block, 0, stream>>>(a);
+      else arz_step_scalar_kernel<T, false><<<(unsigned)grid, block, 0, stream>>>(a);
+    } else if (e->cfg.model == MT_MODEL_LWR) {
+      if (fast) lwr_step_scalar_kernel<T, true><<<(unsigned)grid, block, 0, stream>>>(a);
+      else lwr_step_scalar_kernel<T, false><<<(unsigned)grid, block, 0, stream>>>(a);
+    } else {
+      return fail(MT_EINVAL, "model %d has no step kernel", e->cfg.model);
+    }
+    e->launches++;
+    if (rew) {
+      const int wpb = 8;
+      reward_rows_kernel<T><<<(unsigned)((B + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+          (const T*)obs_out, (T*)reward_out, B, N);
+      e->launches++;
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  return MT_OK;
+}
+
+int step_any(mt_engine* e, const void* obs_in, const void* action, void* obs_out,
+             void* reward_out, cudaStream_t stream) {
+  if (e->params_pending) {
+    if (stream != e->params_stream) CUDA_TRY(cudaStreamWaitEvent(stream, e->params_ready, 0));
+    e->params_pending = false;
+  }
+  if (e->cfg.dtype == MT_F64) return step_typed<double>(e, obs_in, action, obs_out, reward_out, stream);
+  return step_typed<float>(e, obs_in, action, obs_out, reward_out, stream);
+}
+
+bool valid_bc(int bc) { return bc >= MT_BC_LOOP && bc <= MT_BC_HALO; }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int mt_version(void) { return MT_VERSION; }
+
+const char* mt_last_error(void) { return g_err; }
+
+int mt_create(const mt_config* cfg, mt_engine** out) {
+  if (!cfg || !out) return fail(MT_EINVAL, "mt_create: NULL argument");
+  *out = nullptr;
+  if (cfg->model < MT_MODEL_LWR || cfg->model > MT_MODEL_NONLOCAL)
+    return fail(MT_EINVAL, "mt_create: unknown model %d", cfg->model);
+  if (cfg->dtype != MT_F32 && cfg->dtype != MT_F64)
+    return fail(MT_EINVAL, "mt_create: unknown dtype %d", cfg->dtype);
+  if (cfg->n_envs < 1) return fail(MT_EINVAL, "mt_create: n_envs must be >= 1");
+  if (cfg->n_cells < 3 || cfg->n_cells > 0x3fffffff)
+    return fail(MT_EINVAL, "mt_create: n_cells must be in [3, 2^30)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(MT_ECUDA, "mt_create: no CUDA device (this engine has no CPU fallback)");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev)
+    return fail(MT_EINVAL, "mt_create: device %d out of range (%d devices)", cfg->device, ndev);
+  CUDA_TRY(cudaSetDevice(cfg->device));
+  mt_engine* e = new (std::nothrow) mt_engine();
+  if (!e) return fail(MT_ENOMEM, "mt_create: out of host memory");
+  e->cfg = *cfg;
+  e->elt = cfg->dtype == MT_F64 ? 8 : 4;
+  const size_t B = (size_t)cfg->n_envs, N = (size_t)cfg->n_cells;
+  const int V = (int)(16 / e->elt);
+  const Geometry g = plan((long long)B, (int)N, V, true);
+  e->max_tiles = g.tiles;
+  cudaError_t err = cudaMalloc(&e->table, B * TBL_STRIDE * e->elt);
+  if (err == cudaSuccess) err = cudaMalloc((void**)&e->flags, B * sizeof(int));
+  if (err == cudaSuccess && g.tiles > 1) err = cudaMalloc(&e->partial, B * g.tiles * 2 * e->elt);
+  if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+  if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->params_ready, cudaEventDisableTiming);
+  if (err == cudaSuccess && cfg->host_staging) {
+    err = cudaMalloc(&e->d_a, B * 2 * N * e->elt);
+    if (err == cudaSuccess) err = cudaMalloc(&e->d_b, B * 2 * N * e->elt);
+    if (err == cudaSuccess) err = cudaMalloc(&e->d_action, B * e->elt);
+    if (err == cudaSuccess) err = cudaMalloc(&e->d_reward, B * e->elt);
+  }
+  if (err != cudaSuccess) {
+    const int code = err == cudaErrorMemoryAllocation ? MT_ENOMEM : MT_ECUDA;
+    fail(code, "mt_create: %s", cudaGetErrorString(err));
+    mt_destroy(e);
+    return code;
+  }
+  *out = e;
+  return MT_OK;
+}
+
+void mt_destroy(mt_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  cudaFree(e->table);
+  cudaFree(e->flags);
+  cudaFree(e->partial);
+  cudaFree(e->d_a);
+  cudaFree(e->d_b);
+  cudaFree(e->d_action);
+  cudaFree(e->d_reward);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  if (e->params_ready) cudaEventDestroy(e->params_ready);
+  delete e;
+}
+
+int mt_set_params(mt_engine* e, const mt_params* p, void* stream) {
+  if (!e || !p) return fail(MT_EINVAL, "mt_set_params: NULL argument");
+  if (!valid_bc(p->bc_left) || !valid_bc(p->bc_right))
+    return fail(MT_EINVAL, "Unknown boundary conditions: (%d, %d)", p->bc_left, p->bc_right);
+  if (!(p->dx > 0) || !(p->dt > 0)) return fail(MT_EINVAL, "mt_set_params: dx and dt must be > 0");
+  if (e->cfg.model == MT_MODEL_NONLOCAL) {
+    if (p->n_eta < 1 || p->n_eta > e->cfg.max_n_eta || !p->gamma)
+      return fail(MT_EINVAL, "mt_set_params: n_eta=%d outside [1, %d] or gamma NULL",
+                  p->n_eta, e->cfg.max_n_eta);
+  }
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  const long long B = e->cfg.n_envs;
+  const int block = 128;
+  const unsigned grid = (unsigned)((B + block - 1) / block);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (e->cfg.dtype == MT_F64) {
+    ParamArgs<double> a{(double*)e->table, e->flags, B, e->cfg.model, p->rho_max, p->v_max,
+                        p->tau, p->lam, p->rho_crit, p->dt,
+                        (const double*)p->rho_max_env, (const double*)p->v_max_env,
+                        (const double*)p->tau_env, (const double*)p->lam_env,
+                        (const double*)p->rho_crit_env};
+    set_params_kernel<double><<<grid, block, 0, s>>>(a);
+  } else {
+    ParamArgs<float> a{(float*)e->table, e->flags, B, e->cfg.model, p->rho_max, p->v_max,
+                       p->tau, p->lam, p->rho_crit, p->dt,
+                       (const float*)p->rho_max_env, (const float*)p->v_max_env,
+                       (const float*)p->tau_env, (const float*)p->lam_env,
+                       (const float*)p->rho_crit_env};
+    set_params_kernel<float><<<grid, block, 0, s>>>(a);
+  }
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(e->params_ready, s));
+  e->params_stream = s;
+  e->params_pending = true;
+  e->params = *p;
+  e->have_params = true;
+  return MT_OK;
+}
+
+int mt_step(mt_engine* e, const void* obs_in, const void* action, void* obs_out,
+            void* reward_out, void* stream) {
+  if (!e || !obs_in || !obs_out) return fail(MT_EINVAL, "mt_step: NULL argument");
+  if (!e->have_params) return fail(MT_ESTATE, "mt_step: call mt_set_params first");
+  if (obs_in == obs_out) return fail(MT_EINVAL, "mt_step: obs_in and obs_out must differ");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  return step_any(e, obs_in, action, obs_out, reward_out, (cudaStream_t)stream);
+}
+
+int mt_rollout(mt_engine* e, void* obs_a, void* obs_b, const void* actions, void* rewards,
+               int32_t n_steps, void* stream, int32_t* result_in_b) {
+  if (!e || !obs_a || !obs_b) return fail(MT_EINVAL, "mt_rollout: NULL argument");
+  if (!e->have_params) return fail(MT_ESTATE, "mt_rollout: call mt_set_params first");
+  if (obs_a == obs_b) return fail(MT_EINVAL, "mt_rollout: obs_a and obs_b must differ");
+  if (n_steps < 0) return fail(MT_EINVAL, "mt_rollout: n_steps must be >= 0");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  const size_t stride = (size_t)e->cfg.n_envs * e->elt;
+  void* cur = obs_a;
+  void* nxt = obs_b;
+  for (int s = 0; s < n_steps; ++s) {
+    const void* act = actions ? (const char*)actions + (size_t)s * stride : nullptr;
+    void* rew = rewards ? (char*)rewards + (size_t)s * stride : nullptr;
+    const int rc = step_any(e, cur, act, nxt, rew, (cudaStream_t)stream);
+    if (rc != MT_OK) return rc;
+    void* tmp = cur; cur = nxt; nxt = tmp;
+  }
+  if (result_in_b) *result_in_b = (cur == obs_b) ? 1 : 0;
+  return MT_OK;
+}
+
+int mt_step_host(mt_engine* e, const void* obs_in_host, const void* action_host,
+                 void* obs_out_host, void* reward_out_host, int32_t n_steps) {
+  if (!e || !obs_in_host || !obs_out_host) return fail(MT_EINVAL, "mt_step_host: NULL argument");
+  if (!e->have_params) return fail(MT_ESTATE, "mt_step_host: call mt_set_params first");
+  if (!e->d_a) return fail(MT_ESTATE, "mt_step_host: engine created without host_staging");
+  if (n_steps < 1) return fail(MT_EINVAL, "mt_step_host: n_steps must be >= 1");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  const size_t B = (size_t)e->cfg.n_envs, N = (size_t)e->cfg.n_cells;
+  const size_t obs_bytes = B * 2 * N * e->elt, env_bytes = B * e->elt;
+  cudaStream_t s = e->stream;
+  CUDA_TRY(cudaMemcpyAsync(e->d_a, obs_in_host, obs_bytes, cudaMemcpyHostToDevice, s));
+  if (action_host)
+    CUDA_TRY(cudaMemcpyAsync(e->d_action, action_host, env_bytes, cudaMemcpyHostToDevice, s));
+  void* cur = e->d_a;
+  void* nxt = e->d_b;
+  for (int i = 0; i < n_steps; ++i) {
+    void* rew = (reward_out_host && i == n_steps - 1) ? e->d_reward : nullptr;
+    const int rc = step_any(e, cur, action_host ? e->d_action : nullptr, nxt, rew, s);
+    if (rc != MT_OK) return rc;
+    void* tmp = cur; cur = nxt; nxt = tmp;
+  }
+  CUDA_TRY(cudaMemcpyAsync(obs_out_host, cur, obs_bytes, cudaMemcpyDeviceToHost, s));
+  if (reward_out_host)
+    CUDA_TRY(cudaMemcpyAsync(reward_out_host, e->d_reward, env_bytes, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return MT_OK;
+}
+
+int mt_density_sqerr(mt_engine* e, const void* obs_pred, const void* obs_target,
+                     void* out_per_env, void* stream) {
+  if (!e || !obs_pred || !obs_target || !out_per_env)
+    return fail(MT_EINVAL, "mt_density_sqerr: NULL argument");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  const long long B = e->cfg.n_envs;
+  const int N = (int)e->cfg.n_cells, wpb = 8;
+  const unsigned grid = (unsigned)((B + wpb - 1) / wpb);
+  if (e->cfg.dtype == MT_F64)
+    density_sqerr_kernel<double><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(
+        (const double*)obs_pred, (const double*)obs_target, (double*)out_per_env, B, N);
+  else
+    density_sqerr_kernel<float><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(
+        (const float*)obs_pred, (const float*)obs_target, (float*)out_per_env, B, N);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return MT_OK;
+}
+
+int mt_launch_count(const mt_engine* e, int64_t* out) {
+  if (!e || !out) return fail(MT_EINVAL, "mt_launch_count: NULL argument");
+  *out = e->launches;
+  return MT_OK;
+}
+
+int mt_alloc_pinned(uint64_t bytes, void** out) {
+  if (!out) return fail(MT_EINVAL, "mt_alloc_pinned: NULL argument");
+  CUDA_TRY(cudaMallocHost(out, (size_t)bytes));
+  return MT_OK;
+}
+
+int mt_free_pinned(void* p) {
+  CUDA_TRY(cudaFreeHost(p));
+  return MT_OK;
+}
+
+}  // extern "C"

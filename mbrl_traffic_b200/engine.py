@@ -1,0 +1,225 @@
+"""Thin object wrapper over the C ABI (include/mtraffic.h).
+
+``Engine`` owns one ``mt_engine`` handle.  Device buffers are passed as
+``torch`` CUDA tensors (or raw integer addresses); host buffers as NumPy
+arrays.  Nothing here computes: every method is one call into
+``libmtraffic.so``.
+"""
+import ctypes
+
+import numpy as np
+
+from mbrl_traffic_b200 import _lib
+
+_MODELS = {"lwr": _lib.MT_MODEL_LWR, "arz": _lib.MT_MODEL_ARZ,
+           "nonlocal": _lib.MT_MODEL_NONLOCAL}
+_DTYPES = {"float32": _lib.MT_F32, "float64": _lib.MT_F64}
+
+
+def dtype_name(dtype):
+    """Normalise a NumPy / torch / string dtype to 'float32' or 'float64'."""
+    name = str(dtype).replace("torch.", "")
+    if name in ("float32", "float64"):
+        return name
+    name = np.dtype(dtype).name
+    if name not in _DTYPES:
+        raise ValueError("unsupported dtype: {}".format(dtype))
+    return name
+
+
+def parse_boundary_conditions(bc, model, error_prefix=None):
+    """Map the reference's ``boundary_conditions`` value to the ABI codes.
+
+    Accepts the reference's three forms (lwr.py:237-264, arz.py:316-364):
+    ``"loop"``, ``"extend_both"``, ``{"constant_both": (left, right)}`` where
+    each side is a density (LWR, non-local) or a ``(density, relative flow)``
+    pair (ARZ).  Extensions: ``{"inflow_outflow": left}`` (constant upstream,
+    free outflow downstream) and ``{"codes": (left_code, right_code,
+    left_val, right_val)}`` used by the domain-decomposed driver.
+
+    Raises the reference's ``ValueError`` text for anything else.
+    """
+    if error_prefix is None:
+        error_prefix = ("Unknown boundary condition: {}" if model == "arz"
+                        else "Unknown boundary conditions: {}")
+    zero = (0.0, 0.0)
+
+    def pair(x):
+        if model == "arz":
+            return (float(x[0]), float(x[1]))
+        return (float(x), 0.0)
+
+    if isinstance(bc, str) and bc == "loop":
+        return _lib.MT_BC_LOOP, _lib.MT_BC_LOOP, zero, zero
+    if isinstance(bc, str) and bc == "extend_both":
+        return _lib.MT_BC_EXTEND, _lib.MT_BC_EXTEND, zero, zero
+    if isinstance(bc, dict) and len(bc) > 0:
+        key = list(bc.keys())[0]
+        if key == "constant_both":
+            left, right = bc[key][0], bc[key][1]
+            return (_lib.MT_BC_CONSTANT, _lib.MT_BC_CONSTANT,
+                    pair(left), pair(right))
+        if key == "inflow_outflow":
+            return (_lib.MT_BC_CONSTANT, _lib.MT_BC_EXTEND,
+                    pair(bc[key]), zero)
+        if key == "codes":
+            cl, cr, lv, rv = bc[key]
+            return int(cl), int(cr), tuple(lv), tuple(rv)
+    raise ValueError(error_prefix.format(bc))
+
+
+def _ptr(x):
+    """Address of a torch tensor / NumPy array / int, or None."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    raise TypeError("cannot take the address of {!r}".format(type(x)))
+
+
+def _stream_ptr(stream):
+    """cudaStream_t of a torch stream (None -> torch's current stream)."""
+    if isinstance(stream, int):
+        return stream
+    if stream is None:
+        import torch
+        stream = torch.cuda.current_stream()
+    return stream.cuda_stream
+
+
+class Engine(object):
+    """One batched model instance on one GPU (``mt_create`` .. ``mt_destroy``)."""
+
+    def __init__(self, model, dtype, n_envs, n_cells, device=0, max_n_eta=0,
+                 host_staging=False):
+        self._lib = _lib.load()
+        self.model = model
+        self.dtype = dtype_name(dtype)
+        self.n_envs = int(n_envs)
+        self.n_cells = int(n_cells)
+        self.device = int(device)
+        cfg = _lib.MtConfig(
+            model=_MODELS[model], dtype=_DTYPES[self.dtype],
+            n_envs=self.n_envs, n_cells=self.n_cells, device=self.device,
+            max_n_eta=int(max_n_eta), host_staging=int(bool(host_staging)),
+            reserved=0)
+        handle = ctypes.c_void_p()
+        _lib.check(self._lib.mt_create(ctypes.byref(cfg), ctypes.byref(handle)))
+        self._h = handle
+        self._keep = {}  # per-env parameter tensors must outlive the table build
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ #
+    def set_params(self, dx, dt, rho_max, v_max, lam, boundary_conditions,
+                   tau=1.0, rho_crit=None, gamma=None, fast_math=False,
+                   stream=None):
+        """``mt_set_params``.  rho_max / v_max / tau / lam / rho_crit may be
+        Python scalars or device tensors of shape (n_envs,) in the engine
+        dtype; ``gamma`` is a device tensor of look-ahead weights."""
+        p = _lib.MtParams()
+        p.dx, p.dt = float(dx), float(dt)
+        keep = {}
+
+        def put(name, value, default=0.0):
+            if value is None:
+                setattr(p, name, default)
+                setattr(p, name + "_env", None)
+            elif hasattr(value, "data_ptr"):
+                if value.numel() != self.n_envs:
+                    raise ValueError("%s must have n_envs entries" % name)
+                if dtype_name(value.dtype) != self.dtype:
+                    raise ValueError("%s must be %s" % (name, self.dtype))
+                value = value.contiguous()
+                keep[name] = value
+                setattr(p, name, 0.0)
+                setattr(p, name + "_env", value.data_ptr())
+            else:
+                setattr(p, name, float(value))
+                setattr(p, name + "_env", None)
+
+        put("rho_max", rho_max)
+        put("v_max", v_max)
+        put("tau", tau, 1.0)
+        put("lam", lam)
+        put("rho_crit", rho_crit, -1.0)
+        cl, cr, lv, rv = parse_boundary_conditions(boundary_conditions,
+                                                   self.model)
+        p.bc_left, p.bc_right = cl, cr
+        p.bc_left_val[0], p.bc_left_val[1] = lv
+        p.bc_right_val[0], p.bc_right_val[1] = rv
+        if gamma is not None:
+            keep["gamma"] = gamma
+            p.gamma = gamma.data_ptr()
+            p.n_eta = int(gamma.numel())
+        p.flags = _lib.MT_FLAG_FAST_MATH if fast_math else 0
+        _lib.check(self._lib.mt_set_params(self._h, ctypes.byref(p),
+                                           _stream_ptr(stream)))
+        self._keep = keep
+
+    def step(self, obs_in, obs_out, action=None, reward=None, stream=None):
+        """``mt_step`` on device buffers."""
+        _lib.check(self._lib.mt_step(self._h, _ptr(obs_in), _ptr(action),
+                                     _ptr(obs_out), _ptr(reward),
+                                     _stream_ptr(stream)))
+
+    def rollout(self, obs_a, obs_b, n_steps, actions=None, rewards=None,
+                stream=None):
+        """``mt_rollout``; returns the buffer that holds the final state."""
+        flag = ctypes.c_int32(0)
+        _lib.check(self._lib.mt_rollout(
+            self._h, _ptr(obs_a), _ptr(obs_b), _ptr(actions), _ptr(rewards),
+            int(n_steps), _stream_ptr(stream), ctypes.byref(flag)))
+        return obs_b if flag.value else obs_a
+
+    def step_host(self, obs_in, obs_out, action=None, reward=None, n_steps=1):
+        """``mt_step_host`` on NumPy (ideally pinned) buffers; synchronous."""
+        _lib.check(self._lib.mt_step_host(
+            self._h, _ptr(obs_in), _ptr(action), _ptr(obs_out), _ptr(reward),
+            int(n_steps)))
+
+    def density_sqerr(self, obs_pred, obs_target, out, stream=None):
+        """``mt_density_sqerr`` on device buffers."""
+        _lib.check(self._lib.mt_density_sqerr(
+            self._h, _ptr(obs_pred), _ptr(obs_target), _ptr(out),
+            _stream_ptr(stream)))
+
+    @property
+    def launch_count(self):
+        out = ctypes.c_int64(0)
+        _lib.check(self._lib.mt_launch_count(self._h, ctypes.byref(out)))
+        return out.value
+
+
+class PinnedArray(object):
+    """A page-locked NumPy array obtained through ``mt_alloc_pinned``."""
+
+    def __init__(self, shape, dtype):
+        self._lib = _lib.load()
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        p = ctypes.c_void_p()
+        _lib.check(self._lib.mt_alloc_pinned(max(nbytes, 1), ctypes.byref(p)))
+        self._p = p
+        buf = (ctypes.c_char * max(nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype,
+                                   count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._p:
+            self.array = None
+            self._lib.mt_free_pinned(self._p)
+            self._p = None

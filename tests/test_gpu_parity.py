@@ -1,0 +1,436 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the
+golden vectors produced by the reference itself.
+
+Bars: f64 -- LWR and the ARZ density half bit-equal to the
+reference after one step, ARZ velocity within 1e-12 relative (fsolve noise);
+against the closed-form oracle the CUDA result is bit-equal in both halves,
+also after chained steps.  f32 -- stated per test.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import np_oracle as o  # noqa: E402
+
+CASES = load_golden()
+IDS = [c.key for c in CASES]
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device (no CPU fallback exists)")
+
+
+def make_model(kind, **over):
+    from mbrl_traffic_b200 import ARZModel, LWRModel
+    from mbrl_traffic_b200 import ARZ_MODEL_PARAMS, LWR_MODEL_PARAMS
+    base = dict(ARZ_MODEL_PARAMS if kind == "arz" else LWR_MODEL_PARAMS)
+    base.pop("optimizer_cls")
+    extra = {k: over.pop(k) for k in list(over)
+             if k in ("device", "action_is_speed_limit", "fast_math")}
+    base.update({k: v for k, v in over.items() if k in base})
+    cls = ARZModel if kind == "arz" else LWRModel
+    return cls(None, None, None, None, 0, optimizer_cls=None, **base, **extra)
+
+
+def oracle_step(kind, obs, **kw):
+    return (o.arz_step if kind == "arz" else o.lwr_step)(obs, **kw)
+
+
+def make_obs(b, n, rho_max=1.0, v_max=30.0, lam=1, seed=0, dtype=np.float64):
+    rng = np.random.default_rng(1234 + seed)
+    rho = rho_max * rng.uniform(0.05, 0.9, (b, n))
+    v = v_max * (1 - rho / rho_max) ** lam + rng.normal(0, 1.0, (b, n))
+    return np.concatenate((rho, v), axis=1).astype(dtype)
+
+
+def gpu(x):
+    return torch.as_tensor(x, device="cuda:0")
+
+
+# --------------------------------------------------------------------------- #
+# golden vectors from the reference                                           #
+# --------------------------------------------------------------------------- #
+
+@pytest.mark.parametrize("case", CASES, ids=IDS)
+def test_golden_one_step(case):
+    _need_gpu()
+    kw = case.step_kwargs()
+    m = make_model(case.model, **kw)
+    out = m.get_next_obs(gpu(case.obs), None).cpu().numpy()
+    n = out.shape[-1] // 2
+    if case.model == "lwr":
+        assert np.array_equal(out, case.out1)
+    else:
+        assert np.array_equal(out[..., :n], case.out1[..., :n])
+        np.testing.assert_allclose(out[..., n:], case.out1[..., n:],
+                                   rtol=1e-12, atol=1e-12)
+    # and bit-equal to the closed-form oracle in both halves
+    assert np.array_equal(out, oracle_step(case.model, case.obs, **kw))
+    m.close()
+
+
+@pytest.mark.parametrize("case", CASES, ids=IDS)
+def test_golden_chained(case):
+    _need_gpu()
+    kw = case.step_kwargs()
+    m = make_model(case.model, **kw)
+    out = m.run(gpu(case.obs), None, n_steps=case.n_chain).cpu().numpy()
+    cur = case.obs
+    for _ in range(case.n_chain):
+        cur = oracle_step(case.model, cur, **kw)
+    assert np.array_equal(out, cur)                      # vs oracle: bits
+    if case.model == "lwr":
+        assert np.array_equal(out, case.outn)            # vs reference: bits
+    else:
+        np.testing.assert_allclose(out, case.outn, rtol=1e-8, atol=1e-10)
+    m.close()
+
+
+# --------------------------------------------------------------------------- #
+# seeded batches against the oracle                                           #
+# --------------------------------------------------------------------------- #
+
+BCS = {
+    "lwr": ["loop", "extend_both", {"constant_both": (0.3, 0.2)},
+            {"inflow_outflow": 0.25}],
+    "arz": ["loop", "extend_both",
+            {"constant_both": ((0.3, 0.1), (0.2, -0.05))},
+            {"inflow_outflow": (0.25, 0.02)}],
+}
+
+
+def _oracle_bc(kind, bc):
+    """inflow_outflow is an extension; emulate it for the oracle."""
+    return bc
+
+
+def _oracle_with_extension(kind, obs, bc, **kw):
+    if isinstance(bc, dict) and "inflow_outflow" in bc:
+        # constant on the left, extend on the right: compose from the two
+        # reference modes (their cells do not interact within one step)
+        val = bc["inflow_outflow"]
+        right = oracle_step(kind, obs, boundary_conditions="extend_both", **kw)
+        cst = (val, val) if kind == "lwr" else (val, val)
+        left = oracle_step(kind, obs,
+                           boundary_conditions={"constant_both": cst}, **kw)
+        n = obs.shape[1] // 2
+        out = right.copy()
+        out[:, 0] = left[:, 0]
+        out[:, n] = left[:, n]
+        return out
+    return oracle_step(kind, obs, boundary_conditions=bc, **kw)
+
+
+@pytest.mark.parametrize("kind", ["lwr", "arz"])
+@pytest.mark.parametrize("n", [8, 20, 30, 64, 250, 1000, 1024, 4096, 20000])
+@pytest.mark.parametrize("bci", [0, 1, 2, 3])
+def test_batch_matches_oracle_f64(kind, n, bci):
+    _need_gpu()
+    bc = BCS[kind][bci]
+    b = 37 if n <= 1024 else 3
+    obs = make_obs(b, n, seed=n + bci)
+    m = make_model(kind, boundary_conditions=bc)
+    out = m.get_next_obs(gpu(obs), None).cpu().numpy()
+    ref = _oracle_with_extension(kind, obs, bc)
+    assert np.array_equal(out, ref)
+    m.close()
+
+
+@pytest.mark.parametrize("kind", ["lwr", "arz"])
+@pytest.mark.parametrize("n", [3, 5, 7, 33, 1001])
+@pytest.mark.parametrize("bci", [0, 1, 2])
+def test_odd_sizes_use_scalar_kernel(kind, n, bci):
+    _need_gpu()
+    bc = BCS[kind][bci]
+    obs = make_obs(11, n, seed=n)
+    m = make_model(kind, boundary_conditions=bc)
+    out = m.get_next_obs(gpu(obs), None).cpu().numpy()
+    assert np.array_equal(out, oracle_step(kind, obs, boundary_conditions=bc))
+    m.close()
+
+
+@pytest.mark.parametrize("kind", ["lwr", "arz"])
+def test_vector_and_scalar_kernels_agree(kind):
+    """An 8-byte-misaligned buffer forces the scalar kernel."""
+    _need_gpu()
+    from mbrl_traffic_b200.engine import Engine
+    b, n = 16, 256
+    obs = make_obs(b, n, seed=5)
+    eng = Engine(kind, "float64", b, n)
+    eng.set_params(dx=50, dt=0.5, rho_max=1, v_max=30, lam=1,
+                   boundary_conditions="loop", tau=9)
+    x = gpu(obs)
+    out_v = torch.empty_like(x)
+    eng.step(x, out_v)
+    big_in = torch.empty(b * 2 * n + 1, dtype=torch.float64, device="cuda:0")
+    big_out = torch.empty_like(big_in)
+    xin = big_in[1:].view(b, 2 * n)
+    xin.copy_(x)
+    xout = big_out[1:].view(b, 2 * n)
+    assert xin.data_ptr() % 16 == 8
+    eng.step(xin, xout)
+    torch.cuda.synchronize()
+    assert torch.equal(out_v, xout)
+    assert np.array_equal(out_v.cpu().numpy(), oracle_step(kind, obs))
+    eng.close()
+
+
+def test_config2_shape_one_step_bit_exact():
+    """ARZ, 4096 ring envs x 1000 cells (BASELINE.json configs[1])."""
+    _need_gpu()
+    obs = make_obs(4096, 1000, seed=2)
+    m = make_model("arz")
+    out = m.get_next_obs(gpu(obs), None).cpu().numpy()
+    assert np.array_equal(out, o.arz_step(obs))
+    m.close()
+
+
+@pytest.mark.parametrize("kind", ["lwr", "arz"])
+def test_per_env_parameters(kind):
+    _need_gpu()
+    b, n = 64, 200
+    rng = np.random.default_rng(99)
+    rho_max = rng.choice([1.0, 0.2, 0.5, 0.7, 0.13], b)
+    v_max = rng.uniform(10, 35, b)
+    lam = rng.choice([1.0, 2.0, 0.5], b)
+    tau = rng.uniform(2, 25, b)
+    rho = rho_max[:, None] * rng.uniform(0.05, 0.9, (b, n))
+    v = rng.uniform(1, 25, (b, n))
+    obs = np.concatenate((rho, v), axis=1)
+    kw = dict(rho_max=rho_max, v_max=v_max, lam=lam)
+    if kind == "arz":
+        kw["tau"] = tau
+    m = make_model(kind)
+    m.rho_max, m.v_max, m.lam = rho_max, v_max, lam
+    if kind == "arz":
+        m.tau = tau
+        m.rho_crit = rho_max / 2
+        ref = o.arz_step(obs, **kw)
+    else:
+        ref = o.lwr_step(obs, **kw)
+    out = m.get_next_obs(gpu(obs), None).cpu().numpy()
+    assert np.array_equal(out, ref)
+    m.close()
+
+
+def test_general_lambda_is_close():
+    """lam outside {1, 2, 0.5}: pow() is within a few ulp, not bit-equal."""
+    _need_gpu()
+    obs = make_obs(8, 128, lam=1.7, seed=1)
+    for kind in ("lwr", "arz"):
+        m = make_model(kind, lam=1.7)
+        out = m.get_next_obs(gpu(obs), None).cpu().numpy()
+        np.testing.assert_allclose(out, oracle_step(kind, obs, lam=1.7),
+                                   rtol=1e-13, atol=1e-13)
+        m.close()
+
+
+def test_arz_rho_crit_is_frozen_at_construction():
+    _need_gpu()
+    obs = make_obs(4, 64, rho_max=0.4, seed=3)
+    m = make_model("arz")          # rho_max = 1 -> rho_crit = 0.5
+    m.rho_max = 0.4                # like load(): rho_crit stays 0.5
+    out = m.get_next_obs(gpu(obs), None).cpu().numpy()
+    assert np.array_equal(out, o.arz_step(obs, rho_max=0.4, rho_crit=0.5))
+    m.close()
+
+
+def test_attribute_change_is_picked_up():
+    _need_gpu()
+    obs = make_obs(4, 64, seed=4)
+    m = make_model("lwr")
+    a = m.get_next_obs(gpu(obs), None).cpu().numpy()
+    m.v_max = 20
+    m.boundary_conditions = "extend_both"
+    b = m.get_next_obs(gpu(obs), None).cpu().numpy()
+    assert np.array_equal(a, o.lwr_step(obs))
+    assert np.array_equal(
+        b, o.lwr_step(obs, v_max=20, boundary_conditions="extend_both"))
+    m.close()
+
+
+def test_unknown_boundary_condition_raises_like_reference():
+    _need_gpu()
+    obs = make_obs(1, 16)[0]
+    m = make_model("lwr", boundary_conditions="ring")
+    with pytest.raises(ValueError, match="Unknown boundary conditions: ring"):
+        m.get_next_obs(obs, None)
+    m = make_model("arz", boundary_conditions="ring")
+    with pytest.raises(ValueError, match="Unknown boundary condition: ring"):
+        m.get_next_obs(obs, None)
+
+
+# --------------------------------------------------------------------------- #
+# host path, rollouts, rewards, loss                                          #
+# --------------------------------------------------------------------------- #
+
+@pytest.mark.parametrize("kind", ["lwr", "arz"])
+def test_host_path_equals_device_path(kind):
+    _need_gpu()
+    obs = make_obs(32, 1000, seed=6)
+    m = make_model(kind)
+    dev = m.get_next_obs(gpu(obs), None).cpu().numpy()
+    host = m.get_next_obs(obs, None)
+    assert isinstance(host, np.ndarray) and host.dtype == np.float64
+    assert np.array_equal(dev, host)
+    one = m.get_next_obs(obs[0], None)        # 1-D like the reference
+    assert one.shape == (2000,)
+    assert np.array_equal(one, host[0])
+    before = obs.copy()
+    m.get_next_obs(obs, None)
+    assert np.array_equal(obs, before)        # caller's array untouched
+    m.close()
+
+
+@pytest.mark.parametrize("kind", ["lwr", "arz"])
+def test_rollout_equals_repeated_steps(kind):
+    _need_gpu()
+    obs = make_obs(16, 250, seed=7)
+    m = make_model(kind)
+    cur = gpu(obs)
+    for _ in range(25):
+        cur = m.get_next_obs(cur, None)
+    roll = m.run(gpu(obs), None, n_steps=25)
+    assert torch.equal(cur, roll)
+    host = m.run(obs, None, n_steps=25)
+    assert np.array_equal(host, roll.cpu().numpy())
+    ref = obs
+    for _ in range(25):
+        ref = oracle_step(kind, ref)
+    assert np.array_equal(host, ref)
+    m.close()
+
+
+@pytest.mark.parametrize("kind", ["lwr", "arz"])
+@pytest.mark.parametrize("n", [20, 250, 1000, 6000])
+def test_rewards(kind, n):
+    _need_gpu()
+    from mbrl_traffic_b200.engine import Engine
+    b = 19
+    obs = make_obs(b, n, seed=8)
+    eng = Engine(kind, "float64", b, n)
+    eng.set_params(dx=50, dt=0.5, rho_max=1, v_max=30, lam=1,
+                   boundary_conditions="loop", tau=9)
+    x = gpu(obs)
+    out = torch.empty_like(x)
+    rew = torch.empty(b, dtype=torch.float64, device="cuda:0")
+    eng.step(x, out, reward=rew)
+    ref = oracle_step(kind, obs)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    np.testing.assert_allclose(rew.cpu().numpy(), o.mean_speed_reward(ref),
+                               rtol=1e-12)
+    eng.close()
+
+
+def test_action_as_speed_limit():
+    _need_gpu()
+    b, n = 8, 100
+    obs = make_obs(b, n, seed=9)
+    act = np.linspace(12.0, 30.0, b)
+    m = make_model("arz", action_is_speed_limit=True)
+    out = m.get_next_obs(gpu(obs), gpu(act)).cpu().numpy()
+    assert np.array_equal(out, o.arz_step(obs, v_max=act))
+    # default: the action is discarded exactly like the reference
+    m2 = make_model("arz")
+    out2 = m2.get_next_obs(gpu(obs), gpu(act)).cpu().numpy()
+    assert np.array_equal(out2, o.arz_step(obs))
+    m.close()
+    m2.close()
+
+
+@pytest.mark.parametrize("kind", ["lwr", "arz"])
+def test_compute_loss(kind):
+    _need_gpu()
+    b, n = 128, 30
+    obs = make_obs(b, n, seed=10)
+    nxt = make_obs(b, n, seed=11)
+    m = make_model(kind)
+    loss = m.compute_loss(obs, np.zeros((b, 1)), nxt)
+    ref = o.density_mse(nxt, oracle_step(kind, obs))
+    assert abs(loss - ref) <= 1e-12 * abs(ref)
+    # float32 replay-buffer samples, as the reference would feed them
+    loss32 = m.compute_loss(obs.astype(np.float32), np.zeros((b, 1)),
+                            nxt.astype(np.float32))
+    assert abs(loss32 - ref) <= 1e-4 * abs(ref)
+    m.close()
+
+
+# --------------------------------------------------------------------------- #
+# f32 mode                                                                    #
+# --------------------------------------------------------------------------- #
+
+@pytest.mark.parametrize("kind", ["lwr", "arz"])
+@pytest.mark.parametrize("fast", [False, True])
+def test_f32_single_step_tolerance(kind, fast):
+    """f32: every cell within 2e-6 of the f64 oracle applied to the same f32
+    input (relative to max(|ref|, 1) -- densities are O(0.1..1), speeds
+    O(1..30))."""
+    _need_gpu()
+    obs32 = make_obs(256, 1000, seed=12, dtype=np.float32)
+    m = make_model(kind, fast_math=fast)
+    out = m.get_next_obs(gpu(obs32), None).cpu().numpy()
+    assert out.dtype == np.float32
+    ref = oracle_step(kind, obs32.astype(np.float64))
+    err = np.abs(out - ref) / np.maximum(np.abs(ref), 1.0)
+    assert err.max() <= 2e-6, err.max()
+    m.close()
+
+
+def test_f32_exact_mode_matches_numpy_float32():
+    """EXACT f32 arithmetic follows NumPy's float32 evaluation bit for bit."""
+    _need_gpu()
+    obs32 = make_obs(64, 1000, seed=13, dtype=np.float32)
+    m = make_model("lwr")
+    out = m.get_next_obs(gpu(obs32), None).cpu().numpy()
+    ref = o.lwr_step(obs32)
+    assert ref.dtype == np.float32
+    assert np.array_equal(out, ref)
+    m.close()
+
+
+# --------------------------------------------------------------------------- #
+# size-independent properties at full size                                    #
+# --------------------------------------------------------------------------- #
+
+def test_uniform_state_fixed_point_full_size():
+    _need_gpu()
+    b, n = 4096, 1000
+    rho = np.full((b, n), 0.3)
+    obs = np.concatenate((rho, 30 * (1 - rho)), axis=1)
+    for kind in ("lwr", "arz"):
+        m = make_model(kind)
+        out = m.run(gpu(obs), None, n_steps=10).cpu().numpy()
+        np.testing.assert_allclose(out, obs, rtol=0, atol=1e-12)
+        m.close()
+
+
+def test_envs_are_independent_full_size():
+    """Permuting the envs permutes the result (no cross-env coupling)."""
+    _need_gpu()
+    obs = make_obs(4096, 1000, seed=14)
+    perm = np.random.default_rng(0).permutation(4096)
+    m = make_model("arz")
+    a = m.get_next_obs(gpu(obs), None).cpu().numpy()
+    b = m.get_next_obs(gpu(obs[perm]), None).cpu().numpy()
+    assert np.array_equal(a[perm], b)
+    m.close()
+
+
+def test_lwr_interior_mass_telescopes():
+    """sum_{i=1}^{N-2} (rho'_i - rho_i) = -step (f_{N-2} - f_0)."""
+    _need_gpu()
+    obs = make_obs(64, 1000, seed=15)
+    m = make_model("lwr", boundary_conditions="extend_both")
+    out = m.get_next_obs(gpu(obs), None).cpu().numpy()
+    n = 1000
+    f = o.lwr_godunov_flux(obs[:, :n], 30, 1, 1)
+    lhs = (out[:, 1:n - 1] - obs[:, 1:n - 1]).sum(axis=1)
+    rhs = -0.01 * (f[:, n - 2] - f[:, 0])
+    np.testing.assert_allclose(lhs, rhs, rtol=0, atol=1e-11)
+    m.close()

@@ -1,0 +1,161 @@
+"""Host-side contract tests that need no GPU: constructor attributes and
+defaults, model.json schema, boundary-condition parsing, and that the C-ABI
+library loads and exports every symbol include/mtraffic.h declares.
+
+They mirror what the reference's tests pin
+(tests/fast_tests/test_models.py:54-72, 100-162, 194-211, 239-298).
+"""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from mbrl_traffic_b200 import ARZModel, LWRModel, Model
+from mbrl_traffic_b200 import ARZ_MODEL_PARAMS, LWR_MODEL_PARAMS
+from mbrl_traffic_b200 import _lib
+from mbrl_traffic_b200.engine import parse_boundary_conditions
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class DummyOptimizer(object):
+    def __init__(self, **kw):
+        self.kw = kw
+
+
+def _params(base):
+    p = dict(base)
+    p.update(sess=1, ob_space=2, ac_space=3, replay_buffer=4, verbose=5,
+             optimizer_cls=DummyOptimizer)
+    return p
+
+
+def test_model_base_init():
+    m = Model(sess=1, ob_space=2, ac_space=3, replay_buffer=4, verbose=5)
+    assert (m.sess, m.ob_space, m.ac_space, m.replay_buffer, m.verbose) == \
+        (1, 2, 3, 4, 5)
+    for name, args in (("initialize", ()), ("get_next_obs", (0, 0)),
+                       ("update", ()), ("compute_loss", (0, 0, 0)),
+                       ("get_td_map", ()), ("save", ("",)), ("load", ("",))):
+        with pytest.raises(NotImplementedError):
+            getattr(m, name)(*args)
+
+
+def test_default_params_match_reference_values():
+    assert LWR_MODEL_PARAMS == dict(
+        dx=50, dt=0.5, rho_max=1, rho_max_max=1, v_max=30, v_max_max=30,
+        stream_model="greenshield", lam=1, boundary_conditions="loop",
+        optimizer_cls="GeneticAlgorithm")
+    assert ARZ_MODEL_PARAMS == dict(
+        dx=50, dt=0.5, rho_max=1, rho_max_max=1, v_max=30, v_max_max=30,
+        tau=9, tau_max=25, lam=1, boundary_conditions="loop",
+        optimizer_cls="GeneticAlgorithm")
+
+
+def test_arz_init_attributes():
+    m = ARZModel(**_params(ARZ_MODEL_PARAMS))
+    for k in ("dx", "dt", "rho_max", "rho_max_max", "v_max", "v_max_max",
+              "tau", "tau_max", "lam", "boundary_conditions"):
+        assert getattr(m, k) == ARZ_MODEL_PARAMS[k]
+    assert m.optimizer_cls is DummyOptimizer
+    assert m.optimizer_params == {}
+    assert m.rho_crit == 0.5
+    assert m.optimizer.kw["param_low"] == [0, 0, 0, 0]
+    assert m.optimizer.kw["param_high"] == [1, 30, 25, 4]
+    assert m.get_td_map() == {}
+    assert m.initialize() is None
+
+
+def test_lwr_init_attributes():
+    m = LWRModel(**_params(LWR_MODEL_PARAMS))
+    for k in ("dx", "dt", "rho_max", "rho_max_max", "v_max", "v_max_max",
+              "stream_model", "lam", "boundary_conditions"):
+        assert getattr(m, k) == LWR_MODEL_PARAMS[k]
+    assert m.optimizer.kw["param_low"] == [0, 0, 0]
+    assert m.optimizer.kw["param_high"] == [1, 30, 4]
+
+
+@pytest.mark.parametrize("cls,base,keys", [
+    (ARZModel, ARZ_MODEL_PARAMS,
+     ["dx", "dt", "rho_max", "rho_max_max", "v_max", "v_max_max", "tau",
+      "tau_max", "lam", "boundary_conditions"]),
+    (LWRModel, LWR_MODEL_PARAMS,
+     ["dx", "dt", "rho_max", "rho_max_max", "v_max", "v_max_max",
+      "stream_model", "lam", "boundary_conditions"]),
+])
+def test_save_and_load_schema(tmp_path, cls, base, keys):
+    m = cls(**_params(base))
+    for i, k in enumerate(keys):
+        setattr(m, k, i + 1)
+    m.save(str(tmp_path))
+    with open(tmp_path / "model.json") as f:
+        data = json.load(f)
+    assert data == {k: i + 1 for i, k in enumerate(keys)}
+    m2 = cls(**_params(base))
+    m2.load(str(tmp_path / "model.json"))
+    for i, k in enumerate(keys):
+        assert getattr(m2, k) == i + 1
+    if cls is ARZModel:
+        assert m2.rho_crit == 0.5   # frozen at construction (arz.py:199)
+
+
+def test_boundary_condition_parsing():
+    L, E, C = _lib.MT_BC_LOOP, _lib.MT_BC_EXTEND, _lib.MT_BC_CONSTANT
+    assert parse_boundary_conditions("loop", "lwr")[:2] == (L, L)
+    assert parse_boundary_conditions("extend_both", "arz")[:2] == (E, E)
+    assert parse_boundary_conditions({"constant_both": (0.3, 0.2)}, "lwr") == \
+        (C, C, (0.3, 0.0), (0.2, 0.0))
+    assert parse_boundary_conditions(
+        {"constant_both": ((0.3, 0.1), (0.2, -0.05))}, "arz") == \
+        (C, C, (0.3, 0.1), (0.2, -0.05))
+    assert parse_boundary_conditions({"inflow_outflow": 0.25}, "lwr")[:3] == \
+        (C, E, (0.25, 0.0))
+    with pytest.raises(ValueError, match="Unknown boundary conditions: ring"):
+        parse_boundary_conditions("ring", "lwr")
+    with pytest.raises(ValueError, match="Unknown boundary condition: 7"):
+        parse_boundary_conditions(7, "arz")
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    with open(os.path.join(ROOT, "include", "mtraffic.h")) as f:
+        header = f.read()
+    declared = set(re.findall(r"\b(mt_[a-z_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.mt_version() == 100
+
+
+def test_struct_sizes_match_header_layout():
+    import ctypes
+    assert ctypes.sizeof(_lib.MtConfig) == 40
+    assert ctypes.sizeof(_lib.MtParams) == 7 * 8 + 5 * 8 + 8 + 32 + 8 + 8
+
+
+def test_no_cpu_fallback_without_gpu():
+    """Without a CUDA device the product path must fail loudly."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    m = LWRModel(**_params(LWR_MODEL_PARAMS))
+    with pytest.raises(_lib.MtError) as exc:
+        m.get_next_obs(np.full(40, 0.5), None)
+    assert exc.value.code == _lib.MT_ECUDA
+    assert "no CPU fallback" in str(exc.value)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "mbrl_traffic_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for name in files:
+            if name.endswith((".py", ".cu", ".cuh", ".h")):
+                with open(os.path.join(dirpath, name)) as f:
+                    text = f.read()
+                assert "import oracle" not in text and \
+                    "from oracle" not in text, name

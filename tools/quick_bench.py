@@ -1,0 +1,91 @@
+"""Developer timing loop for the step kernels (not the contract bench).
+
+    python tools/quick_bench.py [--model arz] [--dtype float64] [--envs 4096]
+                                [--cells 1000] [--sets 4] [--steps 200]
+
+Round-robins over ``--sets`` independent batches so that every step reads its
+input from HBM (working set >> L2), and also reports the chained
+(ping-pong on one batch) rate.
+"""
+import argparse
+import json
+import sys
+import os
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mbrl_traffic_b200.engine import Engine  # noqa: E402
+
+BYTES = {"arz": 4, "lwr": 3, "nonlocal": 3}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default="arz")
+    ap.add_argument("--dtype", default="float64")
+    ap.add_argument("--envs", type=int, default=4096)
+    ap.add_argument("--cells", type=int, default=1000)
+    ap.add_argument("--sets", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--fast", action="store_true")
+    ap.add_argument("--reward", action="store_true")
+    ap.add_argument("--rho-max", type=float, default=1.0)
+    args = ap.parse_args()
+
+    tdt = torch.float64 if args.dtype == "float64" else torch.float32
+    b, n = args.envs, args.cells
+    eng = Engine(args.model, args.dtype, b, n)
+    eng.set_params(dx=50, dt=0.5, rho_max=args.rho_max, v_max=30, lam=1,
+                   boundary_conditions="loop", tau=9, fast_math=args.fast)
+    rng = np.random.default_rng(0)
+    rho = args.rho_max * rng.uniform(0.05, 0.9, (b, n))
+    v = 30 * (1 - rho / args.rho_max) + rng.normal(0, 1, (b, n))
+    obs = torch.as_tensor(np.concatenate((rho, v), 1), device="cuda").to(tdt)
+    ins = [obs.clone() for _ in range(args.sets)]
+    outs = [torch.empty_like(obs) for _ in range(args.sets)]
+    rew = torch.empty(b, dtype=tdt, device="cuda") if args.reward else None
+    esz = obs.element_size()
+    cells = b * n
+
+    def run(k, chained):
+        if chained:
+            a, c = ins[0], outs[0]
+            for _ in range(k):
+                eng.step(a, c, reward=rew)
+                a, c = c, a
+        else:
+            for i in range(k):
+                j = i % args.sets
+                eng.step(ins[j], outs[j], reward=rew)
+
+    res = {}
+    for chained in (False, True):
+        run(args.warmup, chained)
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(3):
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            run(args.steps, chained)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            best = ms if best is None else min(best, ms)
+        cu = cells / (best * 1e-3)
+        gbs = cu * BYTES[args.model] * esz / 1e9
+        res["chained" if chained else "streaming"] = dict(
+            ms_per_step=round(best, 5), gcups=round(cu / 1e9, 2),
+            algo_GBps=round(gbs, 1), frac_of_6545=round(gbs / 6545.6, 3))
+        if chained:
+            ins[0].copy_(obs)
+    print(json.dumps(dict(model=args.model, dtype=args.dtype, envs=b, cells=n,
+                          fast=args.fast, reward=args.reward,
+                          rho_max=args.rho_max, **res)))
+
+
+if __name__ == "__main__":
+    main()
