@@ -12,7 +12,9 @@
 // mt_math.cuh and below; the C ABI is documented in include/mtraffic.h.
 #include "mtraffic.h"
 #include "mt_math.cuh"
+#include "mt_pipe.cuh"
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -184,7 +186,7 @@ arz_step_vec_kernel(const StepArgs<T> a) {
     unpack(__ldg(reinterpret_cast<const VT*>(row) + w.vec), rho);
     unpack(__ldg(reinterpret_cast<const VT*>(row + N) + w.vec), v);
 #pragma unroll
-    for (int k = 0; k < V; ++k) arz_cell<T, FAST>(e, rho[k], v[k], y[k], r[k], D[k], S[k]);
+    for (int k = 0; k < V; ++k) arz_cell<T, FAST, LAM_RUNTIME>(e, rho[k], v[k], y[k], r[k], D[k], S[k]);
     sS[t] = S[0];
     sD[t] = D[V - 1];
     sR[t] = r[V - 1];
@@ -202,7 +204,7 @@ arz_step_vec_kernel(const StepArgs<T> a) {
     } else if (w.tile_last) {
       const int j = (w.vec + 1) * V;
       T yy, rr, dd;
-      arz_cell<T, FAST>(e, __ldg(row + j), __ldg(row + N + j), yy, rr, dd, S_right);
+      arz_cell<T, FAST, LAM_RUNTIME>(e, __ldg(row + j), __ldg(row + N + j), yy, rr, dd, S_right);
     } else {
       S_right = sS[t + 1];
     }
@@ -222,7 +224,7 @@ arz_step_vec_kernel(const StepArgs<T> a) {
       if (w.tile_first) {
         const int j = w.vec * V - 1;
         T yy, ss;
-        arz_cell<T, FAST>(e, __ldg(row + j), __ldg(row + N + j), yy, r_left, D_left, ss);
+        arz_cell<T, FAST, LAM_RUNTIME>(e, __ldg(row + j), __ldg(row + N + j), yy, r_left, D_left, ss);
       } else {
         D_left = sD[t - 1];
         r_left = sR[t - 1];
@@ -242,7 +244,7 @@ arz_step_vec_kernel(const StepArgs<T> a) {
       if (a.bc_l == MT_BC_LOOP) {            // old state of the last cell
         const T rl = __ldg(row + N - 1), vl = __ldg(row + 2 * N - 1);
         rn[0] = rl;
-        yn[0] = arz_y<T, FAST>(e, rl, vl);
+        yn[0] = arz_y<T, FAST, LAM_RUNTIME>(e, rl, vl);
       } else if (a.bc_l == MT_BC_EXTEND) {   // new state of cell 1
         rn[0] = rn[1];
         yn[0] = yn[1];
@@ -271,7 +273,7 @@ arz_step_vec_kernel(const StepArgs<T> a) {
     }
 #pragma unroll
     for (int k = 0; k < V; ++k) {
-      arz_u<T, FAST>(e, rn[k], yn[k], vn[k]);
+      arz_u<T, FAST, LAM_RUNTIME>(e, rn[k], yn[k], vn[k]);
       if (REWARD) { num += rn[k] * vn[k]; den += rn[k]; }
     }
     T* orow = a.out + w.env * (2LL * N);
@@ -304,7 +306,7 @@ lwr_step_vec_kernel(const StepArgs<T> a) {
     row = a.in + w.env * (2LL * N);   // the velocity half is ignored (lwr.py:197)
     unpack(__ldg(reinterpret_cast<const VT*>(row) + w.vec), rho);
 #pragma unroll
-    for (int k = 0; k < V; ++k) lwr_cell<T, FAST>(e, rho[k], D[k], S[k]);
+    for (int k = 0; k < V; ++k) lwr_cell<T, FAST, LAM_RUNTIME>(e, rho[k], D[k], S[k]);
     sS[t] = S[0];
     sD[t] = D[V - 1];
   }
@@ -318,7 +320,7 @@ lwr_step_vec_kernel(const StepArgs<T> a) {
       S_right = S[V - 1];                               // lwr.py:294
     } else if (w.tile_last) {
       T dd;
-      lwr_cell<T, FAST>(e, __ldg(row + (w.vec + 1) * V), dd, S_right);
+      lwr_cell<T, FAST, LAM_RUNTIME>(e, __ldg(row + (w.vec + 1) * V), dd, S_right);
     } else {
       S_right = sS[t + 1];
     }
@@ -333,7 +335,7 @@ lwr_step_vec_kernel(const StepArgs<T> a) {
       T D_left;
       if (w.tile_first) {
         T ss;
-        lwr_cell<T, FAST>(e, __ldg(row + w.vec * V - 1), D_left, ss);
+        lwr_cell<T, FAST, LAM_RUNTIME>(e, __ldg(row + w.vec * V - 1), D_left, ss);
       } else {
         D_left = sD[t - 1];
       }
@@ -351,8 +353,8 @@ lwr_step_vec_kernel(const StepArgs<T> a) {
       if (a.bc_l == MT_BC_LOOP) {     // UPDATED value of the last cell
         const T r2 = __ldg(row + N - 2), r1 = __ldg(row + N - 1);
         T D2, S2, D1, S1;
-        lwr_cell<T, FAST>(e, r2, D2, S2);
-        lwr_cell<T, FAST>(e, r1, D1, S1);
+        lwr_cell<T, FAST, LAM_RUNTIME>(e, r2, D2, S2);
+        lwr_cell<T, FAST, LAM_RUNTIME>(e, r1, D1, S1);
         rn[0] = lwr_advance<T, FAST>(e, r1, npmin(D1, S1), npmin(D2, S1));
       } else if (a.bc_l == MT_BC_CONSTANT) {
         rn[0] = a.bl0;
@@ -371,7 +373,7 @@ lwr_step_vec_kernel(const StepArgs<T> a) {
     }
 #pragma unroll
     for (int k = 0; k < V; ++k) {
-      vn[k] = v_eq<T, FAST>(rn[k], e);                  // lwr.py:201
+      vn[k] = v_eq<T, FAST, LAM_RUNTIME>(rn[k], e);                  // lwr.py:201
       if (REWARD) { num += rn[k] * vn[k]; den += rn[k]; }
     }
     T* orow = a.out + w.env * (2LL * N);
@@ -392,9 +394,9 @@ __device__ __forceinline__ void arz_interior(const EnvC<T>& e, const T* __restri
                                              int j, T& rho_n, T& y_n) {
   using A = Ar<T, FAST>;
   T yL, rL, DL, SL, yC, rC, DC, SC, yR, rR, DR, SR;
-  arz_cell<T, FAST>(e, __ldg(row + j - 1), __ldg(row + N + j - 1), yL, rL, DL, SL);
-  arz_cell<T, FAST>(e, __ldg(row + j), __ldg(row + N + j), yC, rC, DC, SC);
-  arz_cell<T, FAST>(e, __ldg(row + j + 1), __ldg(row + N + j + 1), yR, rR, DR, SR);
+  arz_cell<T, FAST, LAM_RUNTIME>(e, __ldg(row + j - 1), __ldg(row + N + j - 1), yL, rL, DL, SL);
+  arz_cell<T, FAST, LAM_RUNTIME>(e, __ldg(row + j), __ldg(row + N + j), yC, rC, DC, SC);
+  arz_cell<T, FAST, LAM_RUNTIME>(e, __ldg(row + j + 1), __ldg(row + N + j + 1), yR, rR, DR, SR);
   const T Q = npmin(DC, SR), Qm = npmin(DL, SC);
   const T P = A::mul(Q, rC), Pm = A::mul(Qm, rL);
   arz_advance<T, FAST>(e, __ldg(row + j), yC, Qm, Q, Pm, P, rho_n, y_n);
@@ -414,19 +416,19 @@ __global__ void arz_step_scalar_kernel(const StepArgs<T> a) {
   const T* row = a.in + env * (2LL * N);
   T rn, yn, vn;
   if (i == 0) {
-    if (a.bc_l == MT_BC_LOOP) { rn = row[N - 1]; yn = arz_y<T, FAST>(e, rn, row[2 * N - 1]); }
+    if (a.bc_l == MT_BC_LOOP) { rn = row[N - 1]; yn = arz_y<T, FAST, LAM_RUNTIME>(e, rn, row[2 * N - 1]); }
     else if (a.bc_l == MT_BC_EXTEND) arz_interior<T, FAST>(e, row, N, 1, rn, yn);
     else if (a.bc_l == MT_BC_CONSTANT) { rn = a.bl0; yn = a.bl1; }
-    else { rn = row[0]; yn = arz_y<T, FAST>(e, rn, row[N]); }
+    else { rn = row[0]; yn = arz_y<T, FAST, LAM_RUNTIME>(e, rn, row[N]); }
   } else if (i == N - 1) {
-    if (a.bc_r == MT_BC_LOOP) { rn = row[N - 2]; yn = arz_y<T, FAST>(e, rn, row[2 * N - 2]); }
+    if (a.bc_r == MT_BC_LOOP) { rn = row[N - 2]; yn = arz_y<T, FAST, LAM_RUNTIME>(e, rn, row[2 * N - 2]); }
     else if (a.bc_r == MT_BC_EXTEND) arz_interior<T, FAST>(e, row, N, N - 2, rn, yn);
     else if (a.bc_r == MT_BC_CONSTANT) { rn = a.br0; yn = a.br1; }
-    else { rn = row[N - 1]; yn = arz_y<T, FAST>(e, rn, row[2 * N - 1]); }
+    else { rn = row[N - 1]; yn = arz_y<T, FAST, LAM_RUNTIME>(e, rn, row[2 * N - 1]); }
   } else {
     arz_interior<T, FAST>(e, row, N, i, rn, yn);
   }
-  arz_u<T, FAST>(e, rn, yn, vn);
+  arz_u<T, FAST, LAM_RUNTIME>(e, rn, yn, vn);
   T* orow = a.out + env * (2LL * N);
   orow[i] = rn;
   orow[N + i] = vn;
@@ -437,11 +439,11 @@ template <typename T, bool FAST>
 __device__ __forceinline__ T lwr_scheme(const EnvC<T>& e, const T* __restrict__ row, int N, int j) {
   T DC, SC, DL = 0, SL, DR, SR;
   const T rc = __ldg(row + j);
-  lwr_cell<T, FAST>(e, rc, DC, SC);
-  if (j + 1 < N) lwr_cell<T, FAST>(e, __ldg(row + j + 1), DR, SR); else SR = SC;
+  lwr_cell<T, FAST, LAM_RUNTIME>(e, rc, DC, SC);
+  if (j + 1 < N) lwr_cell<T, FAST, LAM_RUNTIME>(e, __ldg(row + j + 1), DR, SR); else SR = SC;
   const T f = npmin(DC, SR);
   T fm = f;
-  if (j > 0) { lwr_cell<T, FAST>(e, __ldg(row + j - 1), DL, SL); fm = npmin(DL, SC); }
+  if (j > 0) { lwr_cell<T, FAST, LAM_RUNTIME>(e, __ldg(row + j - 1), DL, SL); fm = npmin(DL, SC); }
   return lwr_advance<T, FAST>(e, rc, f, fm);
 }
 
@@ -471,7 +473,7 @@ __global__ void lwr_step_scalar_kernel(const StepArgs<T> a) {
   }
   T* orow = a.out + env * (2LL * N);
   orow[i] = rn;
-  orow[N + i] = v_eq<T, FAST>(rn, e);
+  orow[N + i] = v_eq<T, FAST, LAM_RUNTIME>(rn, e);
 }
 
 // reward for the scalar path: one warp per env over the finished output
@@ -580,8 +582,15 @@ struct mt_engine {
   int* flags = nullptr;   // [B]
   void* partial = nullptr;
   int max_tiles = 1;
+  int sm_count = 148;
   bool have_params = false;
   mt_params params;       // last set
+  // all-scalar parameter sets with lam in {1, 2, 0.5}: constants for the
+  // UNIFORM kernel instantiations (host arithmetic == device arithmetic)
+  bool uniform = false;
+  int lamk = LAM_RUNTIME;
+  UniformC<double> u64;
+  UniformC<float> u32;
   int64_t launches = 0;
   // table readiness: recorded by mt_set_params, awaited once by the next
   // step issued on a different stream
@@ -623,6 +632,75 @@ Geometry plan(long long B, int N, int V, bool aligned) {
   return g;
 }
 
+template <typename T, int MODEL, bool FAST, int LAMK, bool UNIFORM>
+int launch_pipe(const PipeArgs<T>& pa, int grid, cudaStream_t stream) {
+  static bool configured = false;  // per instantiation; the attribute is per function
+  const size_t smem = sizeof(PipeSmem<T>);
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(step_pipe_kernel<T, MODEL, FAST, LAMK, UNIFORM>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  step_pipe_kernel<T, MODEL, FAST, LAMK, UNIFORM><<<grid, PIPE_BLOCK, smem, stream>>>(pa);
+  return MT_OK;
+}
+
+template <typename T, int MODEL, bool FAST>
+int launch_pipe_lam(const PipeArgs<T>& pa, int grid, bool uniform, int lamk, cudaStream_t s) {
+  if (uniform && lamk == LAM_ONE) return launch_pipe<T, MODEL, FAST, LAM_ONE, true>(pa, grid, s);
+  if (uniform && lamk == LAM_TWO) return launch_pipe<T, MODEL, FAST, LAM_TWO, true>(pa, grid, s);
+  if (uniform && lamk == LAM_HALF) return launch_pipe<T, MODEL, FAST, LAM_HALF, true>(pa, grid, s);
+  return launch_pipe<T, MODEL, FAST, LAM_RUNTIME, false>(pa, grid, s);
+}
+
+template <typename T> struct FastAllowed { static constexpr bool value = false; };
+template <> struct FastAllowed<float> { static constexpr bool value = true; };
+
+template <typename T, int MODEL>
+int launch_pipe_model(const PipeArgs<T>& pa, int grid, bool fast, bool uniform, int lamk,
+                      cudaStream_t s) {
+  if constexpr (FastAllowed<T>::value) {
+    if (fast) return launch_pipe_lam<T, MODEL, true>(pa, grid, uniform, lamk, s);
+  }
+  return launch_pipe_lam<T, MODEL, false>(pa, grid, uniform, lamk, s);
+}
+
+template <typename T> const UniformC<T>& uniform_of(const mt_engine* e);
+template <> const UniformC<double>& uniform_of<double>(const mt_engine* e) { return e->u64; }
+template <> const UniformC<float>& uniform_of<float>(const mt_engine* e) { return e->u32; }
+
+bool host_is_pow2(double x) {
+  int ex;
+  return x > 0 && frexp(x, &ex) == 0.5;
+}
+
+// Host restatement of set_params_kernel for an all-scalar parameter set with
+// lam in {1, 2, 0.5}: +, -, *, / and sqrt are IEEE on both sides, so these
+// constants equal the device table bit for bit.
+template <typename T>
+void make_uniform(UniformC<T>& u, int& lamk, int model, const mt_params& p) {
+  const T rho_max = (T)p.rho_max, v_max = (T)p.v_max, lam = (T)p.lam;
+  T rho_crit;
+  if (model == MT_MODEL_ARZ && p.rho_crit >= 0) rho_crit = (T)p.rho_crit;
+  else rho_crit = rho_max / T(2);
+  const T c = (T)(1.0 + p.dt / p.tau);
+  lamk = lam == T(1) ? LAM_ONE : lam == T(2) ? LAM_TWO : lam == T(0.5) ? LAM_HALF : LAM_GENERAL;
+  const T base = T(1) - rho_crit / rho_max;
+  T g = base;
+  if (lamk == LAM_TWO) g = base * base;
+  else if (lamk == LAM_HALF) g = std::sqrt(base);
+  u.rho_max = rho_max;
+  u.inv_rho_max = T(1) / rho_max;
+  u.v_max = v_max;
+  u.lam = lam;
+  u.rho_crit = rho_crit;
+  u.g_crit = g;
+  u.c = c;
+  u.inv_c = T(1) / c;
+  u.flags = lamk | (host_is_pow2((double)rho_max) ? FLAG_RHO_MAX_POW2 : 0) |
+            (host_is_pow2((double)c) ? FLAG_C_POW2 : 0);
+}
+
 template <typename T>
 int step_typed(mt_engine* e, const void* obs_in, const void* action, void* obs_out,
                void* reward_out, cudaStream_t stream) {
@@ -658,7 +736,30 @@ int step_typed(mt_engine* e, const void* obs_in, const void* action, void* obs_o
 
   const bool rew = reward_out != nullptr;
   if (g.grid > 0x7fffffffLL) return fail(MT_EINVAL, "batch too large for one launch");
-  if (g.vector_ok) {
+  if (g.vector_ok && g.tiles == 1 && !(p.flags & MT_FLAG_NO_PIPELINE) &&
+      (e->cfg.model == MT_MODEL_ARZ || e->cfg.model == MT_MODEL_LWR)) {
+    // persistent TMA-pipelined kernel: tiles of consecutive roads
+    PipeArgs<T> pa;
+    pa.in = a.in; pa.out = a.out; pa.table = a.table; pa.flags = a.flags;
+    pa.action = a.action; pa.reward = a.reward;
+    pa.B = B; pa.N = N; pa.nvec = g.nvec; pa.tpe = g.tpe;
+    pa.epc = PIPE_BLOCK / g.tpe;
+    const long long n_tiles = (B + pa.epc - 1) / pa.epc;
+    if (n_tiles > 0x7fffffffLL) return fail(MT_EINVAL, "batch too large for one launch");
+    pa.n_tiles = (int)n_tiles;
+    pa.bc_l = a.bc_l; pa.bc_r = a.bc_r; pa.step = a.step;
+    pa.bl0 = a.bl0; pa.bl1 = a.bl1; pa.br0 = a.br0; pa.br1 = a.br1;
+    pa.u = uniform_of<T>(e);
+    const long long slots = 2LL * e->sm_count;
+    const int grid = (int)(n_tiles < slots ? n_tiles : slots);
+    int rc;
+    if (e->cfg.model == MT_MODEL_ARZ)
+      rc = launch_pipe_model<T, 1>(pa, grid, fast, e->uniform, e->lamk, stream);
+    else
+      rc = launch_pipe_model<T, 0>(pa, grid, fast, e->uniform, e->lamk, stream);
+    if (rc != MT_OK) return rc;
+    e->launches++;
+  } else if (g.vector_ok) {
     const dim3 grid((unsigned)g.grid), block(g.block);
 #define MT_LAUNCH(KERNEL)                                                     \
     do {                                                                      \
@@ -748,6 +849,7 @@ int mt_create(const mt_config* cfg, mt_engine** out) {
   mt_engine* e = new (std::nothrow) mt_engine();
   if (!e) return fail(MT_ENOMEM, "mt_create: out of host memory");
   e->cfg = *cfg;
+  cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
   e->elt = cfg->dtype == MT_F64 ? 8 : 4;
   const size_t B = (size_t)cfg->n_envs, N = (size_t)cfg->n_cells;
   const int V = (int)(16 / e->elt);
@@ -826,6 +928,14 @@ int mt_set_params(mt_engine* e, const mt_params* p, void* stream) {
   e->params_pending = true;
   e->params = *p;
   e->have_params = true;
+  e->uniform = !p->rho_max_env && !p->v_max_env && !p->tau_env && !p->lam_env && !p->rho_crit_env;
+  if (e->uniform) {
+    int lamk = LAM_GENERAL;
+    if (e->cfg.dtype == MT_F64) make_uniform<double>(e->u64, lamk, e->cfg.model, *p);
+    else make_uniform<float>(e->u32, lamk, e->cfg.model, *p);
+    e->lamk = lamk;
+    if (lamk == LAM_GENERAL) e->uniform = false;  // pow(): use the device table
+  }
   return MT_OK;
 }
 

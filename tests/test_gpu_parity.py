@@ -215,8 +215,50 @@ def test_per_env_parameters(kind):
     else:
         ref = o.lwr_step(obs, **kw)
     out = m.get_next_obs(gpu(obs), None).cpu().numpy()
-    assert np.array_equal(out, ref)
+    # arbitrary speeds can push rho' past rho_max, where sqrt (lam = 0.5)
+    # is NaN in the reference too
+    assert np.array_equal(out, ref, equal_nan=True)
+    assert np.isnan(ref).mean() < 0.05
     m.close()
+
+
+@pytest.mark.parametrize("kind", ["lwr", "arz"])
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("n", [8, 30, 64, 250, 1000, 1024])
+@pytest.mark.parametrize("bci", [0, 1, 2])
+def test_pipelined_and_direct_kernels_agree(kind, dtype, n, bci):
+    """The persistent TMA-pipelined kernel and the direct kernel are two
+    schedules of the same arithmetic: bit-identical outputs and rewards."""
+    _need_gpu()
+    from mbrl_traffic_b200.engine import Engine
+    if dtype == "float32" and n % 4:
+        pytest.skip("f32 vectors need N % 4 == 0")
+    b = 301   # not a multiple of the roads-per-tile counts: ragged last tile
+    obs = make_obs(b, n, seed=n, dtype=np.dtype(dtype))
+    tdt = torch.float64 if dtype == "float64" else torch.float32
+    outs, rews = [], []
+    for no_pipe in (False, True):
+        eng = Engine(kind, dtype, b, n)
+        eng.set_params(dx=50, dt=0.5, rho_max=1, v_max=30, lam=1,
+                       boundary_conditions=BCS[kind][bci], tau=9,
+                       no_pipeline=no_pipe)
+        x = gpu(obs)
+        out = torch.empty_like(x)
+        rew = torch.empty(b, dtype=tdt, device="cuda:0")
+        eng.step(x, out, reward=rew)
+        out2 = torch.empty_like(x)
+        eng.step(x, out2)
+        torch.cuda.synchronize()
+        assert torch.equal(out, out2)      # reward variant == plain variant
+        outs.append(out)
+        rews.append(rew)
+        eng.close()
+    assert torch.equal(outs[0], outs[1])
+    assert torch.equal(rews[0], rews[1])
+    if dtype == "float64":
+        assert np.array_equal(outs[0].cpu().numpy(),
+                              oracle_step(kind, obs,
+                                          boundary_conditions=BCS[kind][bci]))
 
 
 def test_general_lambda_is_close():

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--fast", action="store_true")
     ap.add_argument("--reward", action="store_true")
+    ap.add_argument("--direct", action="store_true")
     ap.add_argument("--rho-max", type=float, default=1.0)
     args = ap.parse_args()
 
@@ -39,7 +40,8 @@ def main():
     b, n = args.envs, args.cells
     eng = Engine(args.model, args.dtype, b, n)
     eng.set_params(dx=50, dt=0.5, rho_max=args.rho_max, v_max=30, lam=1,
-                   boundary_conditions="loop", tau=9, fast_math=args.fast)
+                   boundary_conditions="loop", tau=9, fast_math=args.fast,
+                   no_pipeline=args.direct)
     rng = np.random.default_rng(0)
     rho = args.rho_max * rng.uniform(0.05, 0.9, (b, n))
     v = 30 * (1 - rho / args.rho_max) + rng.normal(0, 1, (b, n))
@@ -83,7 +85,7 @@ def main():
         if chained:
             ins[0].copy_(obs)
     print(json.dumps(dict(model=args.model, dtype=args.dtype, envs=b, cells=n,
-                          fast=args.fast, reward=args.reward,
+                          fast=args.fast, reward=args.reward, direct=args.direct,
                           rho_max=args.rho_max, **res)))
 
 
