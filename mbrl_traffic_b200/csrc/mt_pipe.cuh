@@ -19,6 +19,7 @@
 #include <stdint.h>
 #include "mtraffic.h"
 #include "mt_math.cuh"
+#include "mt_cell.cuh"
 
 namespace mt {
 
@@ -81,13 +82,18 @@ template <int N> __device__ __forceinline__ void bulk_wait_read() {
 }
 
 // ---- shared-memory layout ---------------------------------------------------
+constexpr int PIPE_MAX_EPC = 64;                       // roads per tile (cap)
+constexpr int PIPE_XCH = PIPE_BLOCK + PIPE_MAX_EPC + 8;  // one pad slot per road in the tile
+
 template <typename T> struct PipeSmem {
   alignas(128) unsigned char in[PIPE_STAGES][PIPE_TILE_BYTES];
   alignas(128) unsigned char out[PIPE_OUT][PIPE_TILE_BYTES];
-  T xS[PIPE_BLOCK], xD[PIPE_BLOCK], xR[PIPE_BLOCK];  // edge exchange
+  T xS[PIPE_XCH], xD[PIPE_XCH], xR[PIPE_XCH];  // edge exchange
   T s_num[PIPE_BLOCK / 32], s_den[PIPE_BLOCK / 32];
   alignas(8) uint64_t full[PIPE_STAGES];
 };
+
+static_assert(sizeof(PipeSmem<double>) <= 113 * 1024, "two CTAs per SM must fit in 227 KB");
 
 template <typename T> struct PipeArgs {
   const T* in;
@@ -98,21 +104,23 @@ template <typename T> struct PipeArgs {
   T* reward;   // nullptr: no reward reduction
   long long B;
   int N;
-  int nvec;    // N / V
+  int nthr;    // threads that own cells in one road: N / CPT
   int tpe;     // threads per road (padded)
   int epc;     // roads per tile
   int n_tiles;
-  int bc_l, bc_r;
+  int block;   // threads per CTA
+  BcArgs<T> bc;
   T step;
-  T bl0, bl1, br0, br1;
   UniformC<T> u;  // used by the UNIFORM instantiations
 };
 
 // MODEL: 0 = LWR, 1 = ARZ.  LAMK: exponent kind fixed at compile time, or
 // LAM_RUNTIME.  UNIFORM: every road shares the scalar parameters in a.u.
-template <typename T, int MODEL, bool FAST, int LAMK, bool UNIFORM>
-__global__ void __launch_bounds__(PIPE_BLOCK, 2) step_pipe_kernel(const PipeArgs<T> a) {
+// U: 16-byte vectors (of each field) per thread; a thread owns U*V cells.
+template <typename T, int MODEL, bool FAST, int LAMK, bool UNIFORM, int U>
+__global__ void __launch_bounds__(PIPE_BLOCK / U, 2) step_pipe_kernel(const PipeArgs<T> a) {
   constexpr int V = Vec<T>::N;
+  constexpr int CPT = U * V;
   constexpr bool ARZ = (MODEL == 1);
   using VT = typename Vec<T>::type;
   using A = Ar<T, FAST>;
@@ -138,6 +146,9 @@ __global__ void __launch_bounds__(PIPE_BLOCK, 2) step_pipe_kernel(const PipeArgs
                             (size_t)tile * a.epc * row_bytes, bytes, &sm.full[s]);
   };
 
+  // pad slots of the exchange arrays stay zero for the kernel's life: they
+  // feed the (discarded) left-face flux of each road's first cell
+  for (int i = t; i < PIPE_XCH; i += blockDim.x) { sm.xD[i] = T(0); sm.xR[i] = T(0); }
   if (t == 0) {
     for (int s = 0; s < PIPE_STAGES; ++s) mbar_init(&sm.full[s], 1);
     fence_mbar_init();
@@ -148,11 +159,12 @@ __global__ void __launch_bounds__(PIPE_BLOCK, 2) step_pipe_kernel(const PipeArgs
     for (int i = 0; i < pre; ++i) issue_load(i);
   }
 
-  // thread -> (road in tile, vector in road); fixed for the kernel's life
+  // thread -> (road in tile, position in road); fixed for the kernel's life
   const int el = t / a.tpe;
-  const int vec = t - el * a.tpe;
-  const bool row_first = (vec == 0), row_last = (vec == a.nvec - 1);
+  const int pos = t - el * a.tpe;
+  const bool row_first = (pos == 0), row_last = (pos == a.nthr - 1);
   const size_t row_off = (size_t)el * 2 * N;
+  const int xi = t + el;  // exchange slot (one pad slot per road)
 
   EnvC<T> e;
   if (UNIFORM) {
@@ -166,7 +178,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK, 2) step_pipe_kernel(const PipeArgs
     const int o = i % PIPE_OUT;
     const int envs_here = tile_envs(tile);
     const long long env = (long long)tile * a.epc + el;
-    const bool active = (el < envs_here) && (vec < a.nvec);
+    const bool active = (el < envs_here) && (pos < a.nthr);
 
     if (active && (!UNIFORM || a.action != nullptr)) {
       // per-road constants (and/or this step's speed limit): issued before the
@@ -178,33 +190,33 @@ __global__ void __launch_bounds__(PIPE_BLOCK, 2) step_pipe_kernel(const PipeArgs
 
     mbar_wait(&sm.full[s], (uint32_t)((i / PIPE_STAGES) & 1));
 
-    T rho[V], v[V], y[V], r[V], D[V], S[V];
+    T rho[CPT], v[CPT], y[CPT], r[CPT], D[CPT], S[CPT];
     T loop_a = 0, loop_b = 0;  // old boundary-source cells for the LOOP rule
     if (active) {
       const T* row = reinterpret_cast<const T*>(sm.in[s]) + row_off;
-      unpack(reinterpret_cast<const VT*>(row)[vec], rho);
-      if (ARZ) {
-        unpack(reinterpret_cast<const VT*>(row + N)[vec], v);
-        bool ok = true;
 #pragma unroll
-        for (int k = 0; k < V; ++k) {
-          arz_cell_nodiv<T, FAST, LAMK>(e, rho[k], v[k], y[k], D[k], S[k]);
-          r[k] = A::div_unchecked(y[k], rho[k]);           // y / rho (arz.py:411)
-          ok &= A::div_safe(y[k], rho[k]);
+      for (int u = 0; u < U; ++u) {
+        T tmp[V];
+        unpack(reinterpret_cast<const VT*>(row)[pos * U + u], tmp);
+#pragma unroll
+        for (int k = 0; k < V; ++k) rho[u * V + k] = tmp[k];
+        if (ARZ) {
+          unpack(reinterpret_cast<const VT*>(row + N)[pos * U + u], tmp);
+#pragma unroll
+          for (int k = 0; k < V; ++k) v[u * V + k] = tmp[k];
         }
-        if (!ok) {
-#pragma unroll
-          for (int k = 0; k < V; ++k) r[k] = A::div(y[k], rho[k]);
-        }
-        sm.xR[t] = r[V - 1];
-        if (row_first && a.bc_l == MT_BC_LOOP) { loop_a = row[N - 1]; loop_b = row[2 * N - 1]; }
-      } else {
-#pragma unroll
-        for (int k = 0; k < V; ++k) lwr_cell<T, FAST, LAMK>(e, rho[k], D[k], S[k]);
-        if (row_first && a.bc_l == MT_BC_LOOP) { loop_a = row[N - 2]; loop_b = row[N - 1]; }
       }
-      sm.xS[t] = S[0];
-      sm.xD[t] = D[V - 1];
+      if (ARZ) {
+        arz_pass1<T, FAST, LAMK, CPT>(e, rho, v, y, r, D, S);
+        sm.xR[xi + 1] = r[CPT - 1];
+        if (row_first) { loop_a = row[N - 1]; loop_b = row[2 * N - 1]; }
+      } else {
+        lwr_pass1<T, FAST, LAMK, CPT>(e, rho, D, S);
+        if (row_first) { loop_a = row[N - 2]; loop_b = row[N - 1]; }
+      }
+      sm.xS[xi] = S[0];
+      sm.xD[xi + 1] = D[CPT - 1];
+      if (row_last) sm.xS[xi + 1] = S[CPT - 1];  // arz.py:405 / lwr.py:294
     }
     // the output stage about to be overwritten must have been drained by the
     // bulk store issued PIPE_OUT tiles ago
@@ -213,84 +225,26 @@ __global__ void __launch_bounds__(PIPE_BLOCK, 2) step_pipe_kernel(const PipeArgs
 
     T num = 0, den = 0;
     if (active) {
-      const T S_right = row_last ? S[V - 1] : sm.xS[t + 1];  // arz.py:405 / lwr.py:294
-      T Q[V];
-#pragma unroll
-      for (int k = 0; k < V - 1; ++k) Q[k] = npmin(D[k], S[k + 1]);  // arz.py:408 / lwr.py:297
-      Q[V - 1] = npmin(D[V - 1], S_right);
-      T Qm = row_first ? Q[0] : npmin(sm.xD[t - 1], S[0]);           // arz.py:414 / lwr.py:231
-      T rn[V], vn[V];
-      if (ARZ) {
-        T P[V], yn[V];
-#pragma unroll
-        for (int k = 0; k < V; ++k) P[k] = A::mul(Q[k], r[k]);       // arz.py:411
-        T Pm = row_first ? P[0] : A::mul(Qm, sm.xR[t - 1]);          // arz.py:415
-#pragma unroll
-        for (int k = 0; k < V; ++k) {
-          arz_advance<T, FAST>(e, rho[k], y[k], Qm, Q[k], Pm, P[k], rn[k], yn[k]);
-          Qm = Q[k];
-          Pm = P[k];
-        }
-        // boundary cells (arz.py:316-360)
-        if (row_first) {
-          if (a.bc_l == MT_BC_LOOP) { rn[0] = loop_a; yn[0] = arz_y<T, FAST, LAMK>(e, loop_a, loop_b); }
-          else if (a.bc_l == MT_BC_EXTEND) { rn[0] = rn[1]; yn[0] = yn[1]; }
-          else if (a.bc_l == MT_BC_CONSTANT) { rn[0] = a.bl0; yn[0] = a.bl1; }
-          else { rn[0] = rho[0]; yn[0] = y[0]; }
-        }
-        if (row_last) {
-          if (a.bc_r == MT_BC_LOOP) { rn[V - 1] = rho[V - 2]; yn[V - 1] = y[V - 2]; }
-          else if (a.bc_r == MT_BC_EXTEND) { rn[V - 1] = rn[V - 2]; yn[V - 1] = yn[V - 2]; }
-          else if (a.bc_r == MT_BC_CONSTANT) { rn[V - 1] = a.br0; yn[V - 1] = a.br1; }
-          else { rn[V - 1] = rho[V - 1]; yn[V - 1] = y[V - 1]; }
-        }
-        // u(): zero patch, y/rho + V(rho)  (arz.py:258-277), divisions batched
-        T qn[V];
-        bool ok = true;
-#pragma unroll
-        for (int k = 0; k < V; ++k) {
-          if (rn[k] == T(0)) rn[k] = T(0.0000000001);
-          qn[k] = A::div_unchecked(yn[k], rn[k]);
-          ok &= A::div_safe(yn[k], rn[k]);
-        }
-        if (!ok) {
-#pragma unroll
-          for (int k = 0; k < V; ++k) qn[k] = A::div(yn[k], rn[k]);
-        }
-#pragma unroll
-        for (int k = 0; k < V; ++k) vn[k] = A::add(qn[k], v_eq<T, FAST, LAMK>(rn[k], e));
-      } else {
-#pragma unroll
-        for (int k = 0; k < V; ++k) {
-          rn[k] = lwr_advance<T, FAST>(e, rho[k], Q[k], Qm);
-          Qm = Q[k];
-        }
-        // boundary cells (lwr.py:237-260); EXTEND keeps the scheme's values
-        const T second_last = rn[V - 2];
-        if (row_first) {
-          if (a.bc_l == MT_BC_LOOP) {  // UPDATED value of the last cell
-            T D2, S2, D1, S1;
-            lwr_cell<T, FAST, LAMK>(e, loop_a, D2, S2);
-            lwr_cell<T, FAST, LAMK>(e, loop_b, D1, S1);
-            rn[0] = lwr_advance<T, FAST>(e, loop_b, npmin(D1, S1), npmin(D2, S1));
-          } else if (a.bc_l == MT_BC_CONSTANT) { rn[0] = a.bl0; }
-          else if (a.bc_l == MT_BC_HALO) { rn[0] = rho[0]; }
-        }
-        if (row_last) {
-          if (a.bc_r == MT_BC_LOOP) rn[V - 1] = second_last;
-          else if (a.bc_r == MT_BC_CONSTANT) rn[V - 1] = a.br0;
-          else if (a.bc_r == MT_BC_HALO) rn[V - 1] = rho[V - 1];
-        }
-#pragma unroll
-        for (int k = 0; k < V; ++k) vn[k] = v_eq<T, FAST, LAMK>(rn[k], e);  // lwr.py:201
-      }
+      T rn[CPT], vn[CPT];
+      if (ARZ)
+        arz_pass2<T, FAST, LAMK, CPT>(e, a.bc, row_first, row_last, rho, v, y, r, D, S,
+                                      sm.xS[xi + 1], sm.xD[xi], sm.xR[xi], loop_a, loop_b, rn, vn);
+      else
+        lwr_pass2<T, FAST, LAMK, CPT>(e, a.bc, row_first, row_last, rho, D, S, sm.xS[xi + 1],
+                                      sm.xD[xi], loop_a, loop_b, rn, vn);
       if (want_reward) {
 #pragma unroll
-        for (int k = 0; k < V; ++k) { num += rn[k] * vn[k]; den += rn[k]; }
+        for (int k = 0; k < CPT; ++k) { num += rn[k] * vn[k]; den += rn[k]; }
       }
       T* orow = reinterpret_cast<T*>(sm.out[o]) + row_off;
-      reinterpret_cast<VT*>(orow)[vec] = pack(rn);
-      reinterpret_cast<VT*>(orow + N)[vec] = pack(vn);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        T tr[V], tv[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) { tr[k] = rn[u * V + k]; tv[k] = vn[u * V + k]; }
+        reinterpret_cast<VT*>(orow)[pos * U + u] = pack(tr);
+        reinterpret_cast<VT*>(orow + N)[pos * U + u] = pack(tv);
+      }
     }
     fence_proxy_async_smem();  // my generic-proxy writes -> visible to the bulk engine
     __syncthreads();           // B
@@ -301,7 +255,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK, 2) step_pipe_kernel(const PipeArgs
       if (i + PIPE_STAGES < n_my) issue_load(i + PIPE_STAGES);
     }
     if (want_reward) {
-      // per-road sum(rho v)/sum(rho); same deterministic order as the direct kernel
+      // per-road sum(rho v)/sum(rho) in a fixed order
       const unsigned full = 0xffffffffu;
       if (a.tpe <= 32) {
         for (int off = a.tpe >> 1; off > 0; off >>= 1) {

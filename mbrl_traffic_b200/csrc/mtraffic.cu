@@ -1,22 +1,24 @@
 // mtraffic.cu -- kernels and C ABI of libmtraffic (sm_100a).
 //
-// One fused kernel per model step: each thread owns one 16-byte vector of
-// consecutive cells (2 x f64 or 4 x f32) of one road, loads rho and v with one
-// coalesced 128-bit load each, derives the per-cell flux ingredients, swaps
-// the three edge values its neighbours need through shared memory (one
-// __syncthreads), applies the finite-volume update, the boundary rule and the
-// (rho, y) -> (rho, v) conversion, and stores one 128-bit vector per field.
-// Rewards are reduced per road with warp shuffles in the same kernel.
+// One fused kernel per model step (mt_pipe.cuh: persistent, TMA-pipelined;
+// mt_direct.cuh: one CTA per road tile).  Each thread owns a few consecutive
+// cells of one road, derives the per-cell flux ingredients, swaps three edge
+// values with its neighbours through shared memory, applies the finite-volume
+// update, the boundary rule and the (rho, y) -> (rho, v) conversion; rewards
+// are reduced per road with warp shuffles in the same kernel.
 //
-// Reference semantics reproduced here are cited function by function in
-// mt_math.cuh and below; the C ABI is documented in include/mtraffic.h.
+// Reference semantics are cited function by function in mt_math.cuh and
+// mt_cell.cuh; the C ABI is documented in include/mtraffic.h.  This file holds
+// the parameter-table kernel, the launch logic and the ABI itself.
 #include "mtraffic.h"
 #include "mt_math.cuh"
 #include "mt_pipe.cuh"
+#include "mt_direct.cuh"
 
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -43,455 +45,6 @@ int fail(int code, const char* fmt, ...) {
     if (_e != cudaSuccess)                                                    \
       return fail(MT_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));  \
   } while (0)
-
-constexpr int MAX_BLOCK = 512;
-
-// ---------------------------------------------------------------------------
-// kernel arguments
-// ---------------------------------------------------------------------------
-template <typename T> struct StepArgs {
-  const T* in;
-  T* out;
-  const T* table;
-  const int* flags;
-  const T* action;    // [B] or nullptr
-  T* reward;          // [B] or nullptr
-  T* partial;         // [B, tiles, 2] scratch when tiles > 1
-  long long B;
-  int N;
-  int nvec;           // N / V (vector kernels)
-  int tpe;            // threads per env (padded) when tiles == 1
-  int epc;            // envs per CTA when tiles == 1
-  int tiles;          // CTAs per env
-  int bc_l, bc_r;
-  T step;
-  T bl0, bl1, br0, br1;  // CONSTANT boundary values
-};
-
-// thread -> (env, vector) mapping shared by the vector kernels
-struct Where {
-  long long env;
-  int vec;
-  int tile;
-  bool active;
-  bool tile_first;  // first thread of a tile of a multi-tile row
-  bool tile_last;
-};
-
-template <typename T>
-__device__ __forceinline__ Where locate(const StepArgs<T>& a) {
-  Where w;
-  const int t = threadIdx.x;
-  if (a.tiles == 1) {
-    const int el = t / a.tpe;
-    w.vec = t - el * a.tpe;
-    w.env = (long long)blockIdx.x * a.epc + el;
-    w.tile = 0;
-    w.active = (el < a.epc) && (w.env < a.B) && (w.vec < a.nvec);
-    w.tile_first = false;
-    w.tile_last = false;
-  } else {
-    w.env = blockIdx.x / a.tiles;
-    w.tile = blockIdx.x - (int)(w.env * a.tiles);
-    w.vec = w.tile * blockDim.x + t;
-    w.active = w.vec < a.nvec;
-    w.tile_first = (t == 0);
-    w.tile_last = (t == (int)blockDim.x - 1);
-  }
-  return w;
-}
-
-// Per-road reward sum(rho v) / sum(rho), deterministic order.
-// tpe <= 32: segmented butterfly inside the warp.  Otherwise warp butterfly,
-// one partial per warp in shared memory, then the road's first thread adds
-// its warps in order.  Multi-tile rows write one partial per tile.
-template <typename T>
-__device__ __forceinline__ void reduce_reward(const StepArgs<T>& a, const Where& w,
-                                              T num, T den, T* s_num, T* s_den) {
-  const unsigned full = 0xffffffffu;
-  const int t = threadIdx.x;
-  if (a.tiles == 1 && a.tpe <= 32) {
-    for (int off = a.tpe >> 1; off > 0; off >>= 1) {
-      num += __shfl_xor_sync(full, num, off);
-      den += __shfl_xor_sync(full, den, off);
-    }
-    if (w.active && w.vec == 0) a.reward[w.env] = num / den;
-    return;
-  }
-  for (int off = 16; off > 0; off >>= 1) {
-    num += __shfl_xor_sync(full, num, off);
-    den += __shfl_xor_sync(full, den, off);
-  }
-  if ((t & 31) == 0) { s_num[t >> 5] = num; s_den[t >> 5] = den; }
-  __syncthreads();
-  if (a.tiles == 1) {
-    if (w.active && w.vec == 0) {
-      const int w0 = t >> 5, nw = a.tpe >> 5;
-      T n = s_num[w0], d = s_den[w0];
-      for (int i = 1; i < nw; ++i) { n += s_num[w0 + i]; d += s_den[w0 + i]; }
-      a.reward[w.env] = n / d;
-    }
-  } else if (t == 0) {
-    const int nw = blockDim.x >> 5;
-    T n = s_num[0], d = s_den[0];
-    for (int i = 1; i < nw; ++i) { n += s_num[i]; d += s_den[i]; }
-    T* p = a.partial + ((long long)w.env * a.tiles + w.tile) * 2;
-    p[0] = n;
-    p[1] = d;
-  }
-}
-
-// one warp per env: fixed-order sum of the per-tile partials
-template <typename T>
-__global__ void reward_finalize_kernel(const T* __restrict__ partial, T* __restrict__ reward,
-                                       long long B, int tiles) {
-  const long long env = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (env >= B) return;
-  const int lane = threadIdx.x & 31;
-  T n = 0, d = 0;
-  for (int i = lane; i < tiles; i += 32) {
-    n += partial[(env * tiles + i) * 2];
-    d += partial[(env * tiles + i) * 2 + 1];
-  }
-  for (int off = 16; off > 0; off >>= 1) {
-    n += __shfl_xor_sync(0xffffffffu, n, off);
-    d += __shfl_xor_sync(0xffffffffu, d, off);
-  }
-  if (lane == 0) reward[env] = n / d;
-}
-
-// ---------------------------------------------------------------------------
-// ARZ step, vector kernel  (ARZModel.get_next_obs, arz.py:205-221)
-// ---------------------------------------------------------------------------
-template <typename T, bool FAST, bool REWARD>
-__global__ void __launch_bounds__(MAX_BLOCK, 2)
-arz_step_vec_kernel(const StepArgs<T> a) {
-  constexpr int V = Vec<T>::N;
-  using VT = typename Vec<T>::type;
-  using A = Ar<T, FAST>;
-  __shared__ T sS[MAX_BLOCK], sD[MAX_BLOCK], sR[MAX_BLOCK];
-  __shared__ T s_num[MAX_BLOCK / 32], s_den[MAX_BLOCK / 32];
-
-  const int t = threadIdx.x;
-  const Where w = locate(a);
-  const int N = a.N;
-
-  EnvC<T> e;
-  T rho[V], v[V], y[V], r[V], D[V], S[V];
-  const T* row = nullptr;
-  if (w.active) {
-    load_env(e, a.table, a.flags, w.env, a.action, a.step);
-    e.qc = A::mul(e.rho_crit, A::mul(e.v_max, e.g_crit));
-    row = a.in + w.env * (2LL * N);
-    unpack(__ldg(reinterpret_cast<const VT*>(row) + w.vec), rho);
-    unpack(__ldg(reinterpret_cast<const VT*>(row + N) + w.vec), v);
-#pragma unroll
-    for (int k = 0; k < V; ++k) arz_cell<T, FAST, LAM_RUNTIME>(e, rho[k], v[k], y[k], r[k], D[k], S[k]);
-    sS[t] = S[0];
-    sD[t] = D[V - 1];
-    sR[t] = r[V - 1];
-  }
-  __syncthreads();
-
-  T num = 0, den = 0;
-  if (w.active) {
-    const bool row_first = (w.vec == 0), row_last = (w.vec == a.nvec - 1);
-    // supply of the cell to the right of my last cell (arz.py:405: the last
-    // cell of the road pairs with its own supply)
-    T S_right;
-    if (row_last) {
-      S_right = S[V - 1];
-    } else if (w.tile_last) {
-      const int j = (w.vec + 1) * V;
-      T yy, rr, dd;
-      arz_cell<T, FAST, LAM_RUNTIME>(e, __ldg(row + j), __ldg(row + N + j), yy, rr, dd, S_right);
-    } else {
-      S_right = sS[t + 1];
-    }
-    T Q[V], P[V];
-#pragma unroll
-    for (int k = 0; k < V - 1; ++k) Q[k] = npmin(D[k], S[k + 1]);  // arz.py:408
-    Q[V - 1] = npmin(D[V - 1], S_right);
-#pragma unroll
-    for (int k = 0; k < V; ++k) P[k] = A::mul(Q[k], r[k]);         // arz.py:411
-    // flux through my left face (arz.py:414-415: cell 0 reuses its own flux)
-    T Qm, Pm;
-    if (row_first) {
-      Qm = Q[0];
-      Pm = P[0];
-    } else {
-      T D_left, r_left;
-      if (w.tile_first) {
-        const int j = w.vec * V - 1;
-        T yy, ss;
-        arz_cell<T, FAST, LAM_RUNTIME>(e, __ldg(row + j), __ldg(row + N + j), yy, r_left, D_left, ss);
-      } else {
-        D_left = sD[t - 1];
-        r_left = sR[t - 1];
-      }
-      Qm = npmin(D_left, S[0]);
-      Pm = A::mul(Qm, r_left);
-    }
-    T rn[V], yn[V], vn[V];
-#pragma unroll
-    for (int k = 0; k < V; ++k) {
-      arz_advance<T, FAST>(e, rho[k], y[k], Qm, Q[k], Pm, P[k], rn[k], yn[k]);
-      Qm = Q[k];
-      Pm = P[k];
-    }
-    // boundary cells (arz.py:316-360)
-    if (row_first) {
-      if (a.bc_l == MT_BC_LOOP) {            // old state of the last cell
-        const T rl = __ldg(row + N - 1), vl = __ldg(row + 2 * N - 1);
-        rn[0] = rl;
-        yn[0] = arz_y<T, FAST, LAM_RUNTIME>(e, rl, vl);
-      } else if (a.bc_l == MT_BC_EXTEND) {   // new state of cell 1
-        rn[0] = rn[1];
-        yn[0] = yn[1];
-      } else if (a.bc_l == MT_BC_CONSTANT) {
-        rn[0] = a.bl0;
-        yn[0] = a.bl1;
-      } else {                               // HALO: ghost, left as is
-        rn[0] = rho[0];
-        yn[0] = y[0];
-      }
-    }
-    if (row_last) {
-      if (a.bc_r == MT_BC_LOOP) {            // old state of cell N-2
-        rn[V - 1] = rho[V - 2];
-        yn[V - 1] = y[V - 2];
-      } else if (a.bc_r == MT_BC_EXTEND) {   // new state of cell N-2
-        rn[V - 1] = rn[V - 2];
-        yn[V - 1] = yn[V - 2];
-      } else if (a.bc_r == MT_BC_CONSTANT) {
-        rn[V - 1] = a.br0;
-        yn[V - 1] = a.br1;
-      } else {
-        rn[V - 1] = rho[V - 1];
-        yn[V - 1] = y[V - 1];
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < V; ++k) {
-      arz_u<T, FAST, LAM_RUNTIME>(e, rn[k], yn[k], vn[k]);
-      if (REWARD) { num += rn[k] * vn[k]; den += rn[k]; }
-    }
-    T* orow = a.out + w.env * (2LL * N);
-    reinterpret_cast<VT*>(orow)[w.vec] = pack(rn);
-    reinterpret_cast<VT*>(orow + N)[w.vec] = pack(vn);
-  }
-  if (REWARD) reduce_reward(a, w, num, den, s_num, s_den);
-}
-
-// ---------------------------------------------------------------------------
-// LWR step, vector kernel  (LWRModel.get_next_obs, lwr.py:192-266)
-// ---------------------------------------------------------------------------
-template <typename T, bool FAST, bool REWARD>
-__global__ void __launch_bounds__(MAX_BLOCK)
-lwr_step_vec_kernel(const StepArgs<T> a) {
-  constexpr int V = Vec<T>::N;
-  using VT = typename Vec<T>::type;
-  __shared__ T sS[MAX_BLOCK], sD[MAX_BLOCK];
-  __shared__ T s_num[MAX_BLOCK / 32], s_den[MAX_BLOCK / 32];
-
-  const int t = threadIdx.x;
-  const Where w = locate(a);
-  const int N = a.N;
-
-  EnvC<T> e;
-  T rho[V], D[V], S[V];
-  const T* row = nullptr;
-  if (w.active) {
-    load_env(e, a.table, a.flags, w.env, a.action, a.step);
-    row = a.in + w.env * (2LL * N);   // the velocity half is ignored (lwr.py:197)
-    unpack(__ldg(reinterpret_cast<const VT*>(row) + w.vec), rho);
-#pragma unroll
-    for (int k = 0; k < V; ++k) lwr_cell<T, FAST, LAM_RUNTIME>(e, rho[k], D[k], S[k]);
-    sS[t] = S[0];
-    sD[t] = D[V - 1];
-  }
-  __syncthreads();
-
-  T num = 0, den = 0;
-  if (w.active) {
-    const bool row_first = (w.vec == 0), row_last = (w.vec == a.nvec - 1);
-    T S_right;
-    if (row_last) {
-      S_right = S[V - 1];                               // lwr.py:294
-    } else if (w.tile_last) {
-      T dd;
-      lwr_cell<T, FAST, LAM_RUNTIME>(e, __ldg(row + (w.vec + 1) * V), dd, S_right);
-    } else {
-      S_right = sS[t + 1];
-    }
-    T f[V];
-#pragma unroll
-    for (int k = 0; k < V - 1; ++k) f[k] = npmin(D[k], S[k + 1]);
-    f[V - 1] = npmin(D[V - 1], S_right);
-    T fm;
-    if (row_first) {
-      fm = f[0];                                        // lwr.py:231
-    } else {
-      T D_left;
-      if (w.tile_first) {
-        T ss;
-        lwr_cell<T, FAST, LAM_RUNTIME>(e, __ldg(row + w.vec * V - 1), D_left, ss);
-      } else {
-        D_left = sD[t - 1];
-      }
-      fm = npmin(D_left, S[0]);
-    }
-    T rn[V], vn[V];
-#pragma unroll
-    for (int k = 0; k < V; ++k) {
-      rn[k] = lwr_advance<T, FAST>(e, rho[k], f[k], fm);
-      fm = f[k];
-    }
-    // boundary cells (lwr.py:237-260).  EXTEND keeps the scheme's own values.
-    const T keep_second_last = rn[V - 2];
-    if (row_first) {
-      if (a.bc_l == MT_BC_LOOP) {     // UPDATED value of the last cell
-        const T r2 = __ldg(row + N - 2), r1 = __ldg(row + N - 1);
-        T D2, S2, D1, S1;
-        lwr_cell<T, FAST, LAM_RUNTIME>(e, r2, D2, S2);
-        lwr_cell<T, FAST, LAM_RUNTIME>(e, r1, D1, S1);
-        rn[0] = lwr_advance<T, FAST>(e, r1, npmin(D1, S1), npmin(D2, S1));
-      } else if (a.bc_l == MT_BC_CONSTANT) {
-        rn[0] = a.bl0;
-      } else if (a.bc_l == MT_BC_HALO) {
-        rn[0] = rho[0];
-      }
-    }
-    if (row_last) {
-      if (a.bc_r == MT_BC_LOOP) {     // UPDATED value of cell N-2
-        rn[V - 1] = keep_second_last;
-      } else if (a.bc_r == MT_BC_CONSTANT) {
-        rn[V - 1] = a.br0;
-      } else if (a.bc_r == MT_BC_HALO) {
-        rn[V - 1] = rho[V - 1];
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < V; ++k) {
-      vn[k] = v_eq<T, FAST, LAM_RUNTIME>(rn[k], e);                  // lwr.py:201
-      if (REWARD) { num += rn[k] * vn[k]; den += rn[k]; }
-    }
-    T* orow = a.out + w.env * (2LL * N);
-    reinterpret_cast<VT*>(orow)[w.vec] = pack(rn);
-    reinterpret_cast<VT*>(orow + N)[w.vec] = pack(vn);
-  }
-  if (REWARD) reduce_reward(a, w, num, den, s_num, s_den);
-}
-
-// ---------------------------------------------------------------------------
-// scalar kernels: any N >= 3, one thread per cell, neighbours re-derived from
-// global memory.  Used when N is not a multiple of the vector width (or the
-// buffers are not 16-byte aligned) and as an independent cross-check of the
-// vector kernels in the tests.
-// ---------------------------------------------------------------------------
-template <typename T, bool FAST>
-__device__ __forceinline__ void arz_interior(const EnvC<T>& e, const T* __restrict__ row, int N,
-                                             int j, T& rho_n, T& y_n) {
-  using A = Ar<T, FAST>;
-  T yL, rL, DL, SL, yC, rC, DC, SC, yR, rR, DR, SR;
-  arz_cell<T, FAST, LAM_RUNTIME>(e, __ldg(row + j - 1), __ldg(row + N + j - 1), yL, rL, DL, SL);
-  arz_cell<T, FAST, LAM_RUNTIME>(e, __ldg(row + j), __ldg(row + N + j), yC, rC, DC, SC);
-  arz_cell<T, FAST, LAM_RUNTIME>(e, __ldg(row + j + 1), __ldg(row + N + j + 1), yR, rR, DR, SR);
-  const T Q = npmin(DC, SR), Qm = npmin(DL, SC);
-  const T P = A::mul(Q, rC), Pm = A::mul(Qm, rL);
-  arz_advance<T, FAST>(e, __ldg(row + j), yC, Qm, Q, Pm, P, rho_n, y_n);
-}
-
-template <typename T, bool FAST>
-__global__ void arz_step_scalar_kernel(const StepArgs<T> a) {
-  using A = Ar<T, FAST>;
-  const int N = a.N;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= a.B * N) return;
-  const long long env = gid / N;
-  const int i = (int)(gid - env * N);
-  EnvC<T> e;
-  load_env(e, a.table, a.flags, env, a.action, a.step);
-  e.qc = A::mul(e.rho_crit, A::mul(e.v_max, e.g_crit));
-  const T* row = a.in + env * (2LL * N);
-  T rn, yn, vn;
-  if (i == 0) {
-    if (a.bc_l == MT_BC_LOOP) { rn = row[N - 1]; yn = arz_y<T, FAST, LAM_RUNTIME>(e, rn, row[2 * N - 1]); }
-    else if (a.bc_l == MT_BC_EXTEND) arz_interior<T, FAST>(e, row, N, 1, rn, yn);
-    else if (a.bc_l == MT_BC_CONSTANT) { rn = a.bl0; yn = a.bl1; }
-    else { rn = row[0]; yn = arz_y<T, FAST, LAM_RUNTIME>(e, rn, row[N]); }
-  } else if (i == N - 1) {
-    if (a.bc_r == MT_BC_LOOP) { rn = row[N - 2]; yn = arz_y<T, FAST, LAM_RUNTIME>(e, rn, row[2 * N - 2]); }
-    else if (a.bc_r == MT_BC_EXTEND) arz_interior<T, FAST>(e, row, N, N - 2, rn, yn);
-    else if (a.bc_r == MT_BC_CONSTANT) { rn = a.br0; yn = a.br1; }
-    else { rn = row[N - 1]; yn = arz_y<T, FAST, LAM_RUNTIME>(e, rn, row[2 * N - 1]); }
-  } else {
-    arz_interior<T, FAST>(e, row, N, i, rn, yn);
-  }
-  arz_u<T, FAST, LAM_RUNTIME>(e, rn, yn, vn);
-  T* orow = a.out + env * (2LL * N);
-  orow[i] = rn;
-  orow[N + i] = vn;
-}
-
-// updated LWR density of cell j under the scheme alone (no boundary rule)
-template <typename T, bool FAST>
-__device__ __forceinline__ T lwr_scheme(const EnvC<T>& e, const T* __restrict__ row, int N, int j) {
-  T DC, SC, DL = 0, SL, DR, SR;
-  const T rc = __ldg(row + j);
-  lwr_cell<T, FAST, LAM_RUNTIME>(e, rc, DC, SC);
-  if (j + 1 < N) lwr_cell<T, FAST, LAM_RUNTIME>(e, __ldg(row + j + 1), DR, SR); else SR = SC;
-  const T f = npmin(DC, SR);
-  T fm = f;
-  if (j > 0) { lwr_cell<T, FAST, LAM_RUNTIME>(e, __ldg(row + j - 1), DL, SL); fm = npmin(DL, SC); }
-  return lwr_advance<T, FAST>(e, rc, f, fm);
-}
-
-template <typename T, bool FAST>
-__global__ void lwr_step_scalar_kernel(const StepArgs<T> a) {
-  const int N = a.N;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= a.B * N) return;
-  const long long env = gid / N;
-  const int i = (int)(gid - env * N);
-  EnvC<T> e;
-  load_env(e, a.table, a.flags, env, a.action, a.step);
-  const T* row = a.in + env * (2LL * N);
-  T rn;
-  if (i == 0) {
-    if (a.bc_l == MT_BC_LOOP) rn = lwr_scheme<T, FAST>(e, row, N, N - 1);
-    else if (a.bc_l == MT_BC_EXTEND) rn = lwr_scheme<T, FAST>(e, row, N, 0);
-    else if (a.bc_l == MT_BC_CONSTANT) rn = a.bl0;
-    else rn = row[0];
-  } else if (i == N - 1) {
-    if (a.bc_r == MT_BC_LOOP) rn = lwr_scheme<T, FAST>(e, row, N, N - 2);
-    else if (a.bc_r == MT_BC_EXTEND) rn = lwr_scheme<T, FAST>(e, row, N, N - 1);
-    else if (a.bc_r == MT_BC_CONSTANT) rn = a.br0;
-    else rn = row[N - 1];
-  } else {
-    rn = lwr_scheme<T, FAST>(e, row, N, i);
-  }
-  T* orow = a.out + env * (2LL * N);
-  orow[i] = rn;
-  orow[N + i] = v_eq<T, FAST, LAM_RUNTIME>(rn, e);
-}
-
-// reward for the scalar path: one warp per env over the finished output
-template <typename T>
-__global__ void reward_rows_kernel(const T* __restrict__ obs, T* __restrict__ reward,
-                                   long long B, int N) {
-  const long long env = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (env >= B) return;
-  const int lane = threadIdx.x & 31;
-  const T* row = obs + env * (2LL * N);
-  T n = 0, d = 0;
-  for (int i = lane; i < N; i += 32) { n += row[i] * row[N + i]; d += row[i]; }
-  for (int off = 16; off > 0; off >>= 1) {
-    n += __shfl_xor_sync(0xffffffffu, n, off);
-    d += __shfl_xor_sync(0xffffffffu, d, off);
-  }
-  if (lane == 0) reward[env] = n / d;
-}
 
 // ---------------------------------------------------------------------------
 // parameter table  (one thread per env)
@@ -632,37 +185,37 @@ Geometry plan(long long B, int N, int V, bool aligned) {
   return g;
 }
 
-template <typename T, int MODEL, bool FAST, int LAMK, bool UNIFORM>
+template <typename T, int MODEL, bool FAST, int LAMK, bool UNIFORM, int U>
 int launch_pipe(const PipeArgs<T>& pa, int grid, cudaStream_t stream) {
   static bool configured = false;  // per instantiation; the attribute is per function
   const size_t smem = sizeof(PipeSmem<T>);
   if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(step_pipe_kernel<T, MODEL, FAST, LAMK, UNIFORM>,
+    CUDA_TRY(cudaFuncSetAttribute(step_pipe_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  step_pipe_kernel<T, MODEL, FAST, LAMK, UNIFORM><<<grid, PIPE_BLOCK, smem, stream>>>(pa);
+  step_pipe_kernel<T, MODEL, FAST, LAMK, UNIFORM, U><<<grid, pa.block, smem, stream>>>(pa);
   return MT_OK;
 }
 
-template <typename T, int MODEL, bool FAST>
+template <typename T, int MODEL, bool FAST, int U>
 int launch_pipe_lam(const PipeArgs<T>& pa, int grid, bool uniform, int lamk, cudaStream_t s) {
-  if (uniform && lamk == LAM_ONE) return launch_pipe<T, MODEL, FAST, LAM_ONE, true>(pa, grid, s);
-  if (uniform && lamk == LAM_TWO) return launch_pipe<T, MODEL, FAST, LAM_TWO, true>(pa, grid, s);
-  if (uniform && lamk == LAM_HALF) return launch_pipe<T, MODEL, FAST, LAM_HALF, true>(pa, grid, s);
-  return launch_pipe<T, MODEL, FAST, LAM_RUNTIME, false>(pa, grid, s);
+  if (uniform && lamk == LAM_ONE) return launch_pipe<T, MODEL, FAST, LAM_ONE, true, U>(pa, grid, s);
+  if (uniform && lamk == LAM_TWO) return launch_pipe<T, MODEL, FAST, LAM_TWO, true, U>(pa, grid, s);
+  if (uniform && lamk == LAM_HALF) return launch_pipe<T, MODEL, FAST, LAM_HALF, true, U>(pa, grid, s);
+  return launch_pipe<T, MODEL, FAST, LAM_RUNTIME, false, U>(pa, grid, s);
 }
 
 template <typename T> struct FastAllowed { static constexpr bool value = false; };
 template <> struct FastAllowed<float> { static constexpr bool value = true; };
 
-template <typename T, int MODEL>
+template <typename T, int MODEL, int U>
 int launch_pipe_model(const PipeArgs<T>& pa, int grid, bool fast, bool uniform, int lamk,
                       cudaStream_t s) {
   if constexpr (FastAllowed<T>::value) {
-    if (fast) return launch_pipe_lam<T, MODEL, true>(pa, grid, uniform, lamk, s);
+    if (fast) return launch_pipe_lam<T, MODEL, true, U>(pa, grid, uniform, lamk, s);
   }
-  return launch_pipe_lam<T, MODEL, false>(pa, grid, uniform, lamk, s);
+  return launch_pipe_lam<T, MODEL, false, U>(pa, grid, uniform, lamk, s);
 }
 
 template <typename T> const UniformC<T>& uniform_of(const mt_engine* e);
@@ -701,6 +254,16 @@ void make_uniform(UniformC<T>& u, int& lamk, int model, const mt_params& p) {
             (host_is_pow2((double)c) ? FLAG_C_POW2 : 0);
 }
 
+// cells per thread of the pipelined kernel: U 16-byte vectors of each field
+int pipe_vectors_per_thread() {
+  static int u = -1;
+  if (u < 0) {
+    const char* s = getenv("MT_PIPE_U");
+    u = (s && s[0] == '1') ? 1 : (s && s[0] == '2') ? 2 : 0;  // 0 = default
+  }
+  return u;
+}
+
 template <typename T>
 int step_typed(mt_engine* e, const void* obs_in, const void* action, void* obs_out,
                void* reward_out, cudaStream_t stream) {
@@ -710,7 +273,58 @@ int step_typed(mt_engine* e, const void* obs_in, const void* action, void* obs_o
   const int N = (int)e->cfg.n_cells;
   const bool aligned = (((uintptr_t)obs_in | (uintptr_t)obs_out) & 15u) == 0;
   const Geometry g = plan(B, N, V, aligned);
-  const bool fast = (p.flags & MT_FLAG_FAST_MATH) != 0;
+  const bool fast = FastAllowed<T>::value && (p.flags & MT_FLAG_FAST_MATH) != 0;
+  const bool rew = reward_out != nullptr;
+
+  BcArgs<T> bc;
+  bc.bc_l = p.bc_left;
+  bc.bc_r = p.bc_right;
+  bc.bl0 = (T)p.bc_left_val[0];
+  bc.bl1 = (T)p.bc_left_val[1];
+  bc.br0 = (T)p.bc_right_val[0];
+  bc.br1 = (T)p.bc_right_val[1];
+  const T step = (T)(p.dt / p.dx);
+
+  if (g.grid > 0x7fffffffLL) return fail(MT_EINVAL, "batch too large for one launch");
+  if (g.vector_ok && g.tiles == 1 && !(p.flags & MT_FLAG_NO_PIPELINE)) {
+    // persistent TMA-pipelined kernel: tiles of consecutive roads
+    int U = pipe_vectors_per_thread();
+    if (U == 0) U = (sizeof(T) == 8) ? 2 : 1;
+    if (N % (U * V) != 0 || N < 2 * U * V) U = 1;
+    PipeArgs<T> pa;
+    pa.in = (const T*)obs_in;
+    pa.out = (T*)obs_out;
+    pa.table = (const T*)e->table;
+    pa.flags = e->flags;
+    pa.action = (const T*)action;
+    pa.reward = (T*)reward_out;
+    pa.B = B;
+    pa.N = N;
+    pa.nthr = N / (U * V);
+    pa.block = PIPE_BLOCK / U;
+    pa.tpe = pa.nthr <= 32 ? next_pow2(pa.nthr) : ((pa.nthr + 31) / 32) * 32;
+    pa.epc = pa.block / pa.tpe;
+    if (pa.epc > PIPE_MAX_EPC) pa.epc = PIPE_MAX_EPC;
+    const long long n_tiles = (B + pa.epc - 1) / pa.epc;
+    if (n_tiles > 0x7fffffffLL) return fail(MT_EINVAL, "batch too large for one launch");
+    pa.n_tiles = (int)n_tiles;
+    pa.bc = bc;
+    pa.step = step;
+    pa.u = uniform_of<T>(e);
+    const long long slots = 2LL * e->sm_count;
+    const int grid = (int)(n_tiles < slots ? n_tiles : slots);
+    int rc;
+    if (e->cfg.model == MT_MODEL_ARZ)
+      rc = U == 2 ? launch_pipe_model<T, 1, 2>(pa, grid, fast, e->uniform, e->lamk, stream)
+                  : launch_pipe_model<T, 1, 1>(pa, grid, fast, e->uniform, e->lamk, stream);
+    else
+      rc = U == 2 ? launch_pipe_model<T, 0, 2>(pa, grid, fast, e->uniform, e->lamk, stream)
+                  : launch_pipe_model<T, 0, 1>(pa, grid, fast, e->uniform, e->lamk, stream);
+    if (rc != MT_OK) return rc;
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return MT_OK;
+  }
 
   StepArgs<T> a;
   a.in = (const T*)obs_in;
@@ -726,55 +340,28 @@ int step_typed(mt_engine* e, const void* obs_in, const void* action, void* obs_o
   a.tpe = g.tpe;
   a.epc = g.epc;
   a.tiles = g.tiles;
-  a.bc_l = p.bc_left;
-  a.bc_r = p.bc_right;
-  a.step = (T)(p.dt / p.dx);
-  a.bl0 = (T)p.bc_left_val[0];
-  a.bl1 = (T)p.bc_left_val[1];
-  a.br0 = (T)p.bc_right_val[0];
-  a.br1 = (T)p.bc_right_val[1];
-
-  const bool rew = reward_out != nullptr;
-  if (g.grid > 0x7fffffffLL) return fail(MT_EINVAL, "batch too large for one launch");
-  if (g.vector_ok && g.tiles == 1 && !(p.flags & MT_FLAG_NO_PIPELINE) &&
-      (e->cfg.model == MT_MODEL_ARZ || e->cfg.model == MT_MODEL_LWR)) {
-    // persistent TMA-pipelined kernel: tiles of consecutive roads
-    PipeArgs<T> pa;
-    pa.in = a.in; pa.out = a.out; pa.table = a.table; pa.flags = a.flags;
-    pa.action = a.action; pa.reward = a.reward;
-    pa.B = B; pa.N = N; pa.nvec = g.nvec; pa.tpe = g.tpe;
-    pa.epc = PIPE_BLOCK / g.tpe;
-    const long long n_tiles = (B + pa.epc - 1) / pa.epc;
-    if (n_tiles > 0x7fffffffLL) return fail(MT_EINVAL, "batch too large for one launch");
-    pa.n_tiles = (int)n_tiles;
-    pa.bc_l = a.bc_l; pa.bc_r = a.bc_r; pa.step = a.step;
-    pa.bl0 = a.bl0; pa.bl1 = a.bl1; pa.br0 = a.br0; pa.br1 = a.br1;
-    pa.u = uniform_of<T>(e);
-    const long long slots = 2LL * e->sm_count;
-    const int grid = (int)(n_tiles < slots ? n_tiles : slots);
-    int rc;
-    if (e->cfg.model == MT_MODEL_ARZ)
-      rc = launch_pipe_model<T, 1>(pa, grid, fast, e->uniform, e->lamk, stream);
-    else
-      rc = launch_pipe_model<T, 0>(pa, grid, fast, e->uniform, e->lamk, stream);
-    if (rc != MT_OK) return rc;
-    e->launches++;
-  } else if (g.vector_ok) {
+  a.bc = bc;
+  a.step = step;
+  const int wpb = 8;  // warps per block of the per-env helper kernels
+  if (g.vector_ok) {
     const dim3 grid((unsigned)g.grid), block(g.block);
-#define MT_LAUNCH(KERNEL)                                                     \
-    do {                                                                      \
-      if (fast) { if (rew) KERNEL<T, true, true><<<grid, block, 0, stream>>>(a);  \
-                  else KERNEL<T, true, false><<<grid, block, 0, stream>>>(a); }   \
-      else { if (rew) KERNEL<T, false, true><<<grid, block, 0, stream>>>(a);      \
-             else KERNEL<T, false, false><<<grid, block, 0, stream>>>(a); }       \
-    } while (0)
-    if (e->cfg.model == MT_MODEL_ARZ) MT_LAUNCH(arz_step_vec_kernel);
-    else if (e->cfg.model == MT_MODEL_LWR) MT_LAUNCH(lwr_step_vec_kernel);
-    else return fail(MT_EINVAL, "model %d has no step kernel", e->cfg.model);
-#undef MT_LAUNCH
+    if (e->cfg.model == MT_MODEL_ARZ) {
+      if constexpr (FastAllowed<T>::value) {
+        if (fast) step_vec_kernel<T, 1, true><<<grid, block, 0, stream>>>(a);
+        else step_vec_kernel<T, 1, false><<<grid, block, 0, stream>>>(a);
+      } else {
+        step_vec_kernel<T, 1, false><<<grid, block, 0, stream>>>(a);
+      }
+    } else {
+      if constexpr (FastAllowed<T>::value) {
+        if (fast) step_vec_kernel<T, 0, true><<<grid, block, 0, stream>>>(a);
+        else step_vec_kernel<T, 0, false><<<grid, block, 0, stream>>>(a);
+      } else {
+        step_vec_kernel<T, 0, false><<<grid, block, 0, stream>>>(a);
+      }
+    }
     e->launches++;
     if (rew && g.tiles > 1) {
-      const int wpb = 8;
       reward_finalize_kernel<T><<<(unsigned)((B + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
           (const T*)e->partial, (T*)reward_out, B, g.tiles);
       e->launches++;
@@ -785,17 +372,14 @@ int step_typed(mt_engine* e, const void* obs_in, const void* action, void* obs_o
     const long long grid = (cells + block - 1) / block;
     if (grid > 0x7fffffffLL) return fail(MT_EINVAL, "batch too large for one launch");
     if (e->cfg.model == MT_MODEL_ARZ) {
-      if (fast) arz_step_scalar_kernel<T, true><<<(unsigned)grid, block, 0, stream>>>(a);
+      if (fast) arz_step_scalar_kernel<T, FastAllowed<T>::value><<<(unsigned)grid, block, 0, stream>>>(a);
       else arz_step_scalar_kernel<T, false><<<(unsigned)grid, block, 0, stream>>>(a);
-    } else if (e->cfg.model == MT_MODEL_LWR) {
-      if (fast) lwr_step_scalar_kernel<T, true><<<(unsigned)grid, block, 0, stream>>>(a);
-      else lwr_step_scalar_kernel<T, false><<<(unsigned)grid, block, 0, stream>>>(a);
     } else {
-      return fail(MT_EINVAL, "model %d has no step kernel", e->cfg.model);
+      if (fast) lwr_step_scalar_kernel<T, FastAllowed<T>::value><<<(unsigned)grid, block, 0, stream>>>(a);
+      else lwr_step_scalar_kernel<T, false><<<(unsigned)grid, block, 0, stream>>>(a);
     }
     e->launches++;
     if (rew) {
-      const int wpb = 8;
       reward_rows_kernel<T><<<(unsigned)((B + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
           (const T*)obs_out, (T*)reward_out, B, N);
       e->launches++;
@@ -811,6 +395,8 @@ int step_any(mt_engine* e, const void* obs_in, const void* action, void* obs_out
     if (stream != e->params_stream) CUDA_TRY(cudaStreamWaitEvent(stream, e->params_ready, 0));
     e->params_pending = false;
   }
+  if (e->cfg.model == MT_MODEL_NONLOCAL)
+    return fail(MT_EINVAL, "the non-local model has no step kernel yet");
   if (e->cfg.dtype == MT_F64) return step_typed<double>(e, obs_in, action, obs_out, reward_out, stream);
   return step_typed<float>(e, obs_in, action, obs_out, reward_out, stream);
 }

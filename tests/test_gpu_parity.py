@@ -254,7 +254,8 @@ def test_pipelined_and_direct_kernels_agree(kind, dtype, n, bci):
         rews.append(rew)
         eng.close()
     assert torch.equal(outs[0], outs[1])
-    assert torch.equal(rews[0], rews[1])
+    # rewards are sums in a kernel-specific (but fixed) order
+    torch.testing.assert_close(rews[0], rews[1], rtol=1e-12 if dtype == "float64" else 1e-5, atol=0)
     if dtype == "float64":
         assert np.array_equal(outs[0].cpu().numpy(),
                               oracle_step(kind, obs,
