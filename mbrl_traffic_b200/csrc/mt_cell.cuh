@@ -30,11 +30,16 @@ __device__ __forceinline__ void arz_pass1(const EnvC<T>& e, const T (&rho)[CPT],
   for (int k = 0; k < CPT; ++k) {
     arz_cell_nodiv<T, FAST, LAMK>(e, rho[k], v[k], y[k], D[k], S[k]);
     r[k] = A::div_unchecked(y[k], rho[k]);  // y / rho (arz.py:411)
-    ok &= A::div_safe(y[k], rho[k]);
+    ok &= A::div_quick(y[k], rho[k]);
   }
-  if (!ok) {  // operands outside the range of the inline expansion: IEEE path
+  if (!ok) {  // rare: an exact zero, or operands outside the inline expansion's range
+    bool ok2 = true;
 #pragma unroll
-    for (int k = 0; k < CPT; ++k) r[k] = A::div(y[k], rho[k]);
+    for (int k = 0; k < CPT; ++k) ok2 &= A::div_safe(y[k], rho[k]);
+    if (!ok2) {
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) r[k] = A::div(y[k], rho[k]);
+    }
   }
 }
 
@@ -71,7 +76,12 @@ __device__ __forceinline__ void arz_pass2(const EnvC<T>& e, const BcArgs<T>& b, 
 #pragma unroll
   for (int k = 0; k < CPT; ++k) {
     vn[k] = A::div_unchecked(yn[k], rn[k]);
-    ok &= A::div_safe(yn[k], rn[k]);
+    ok &= A::div_quick(yn[k], rn[k]);
+  }
+  if (!ok) {  // rare: re-test admitting exact zeros
+    ok = true;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) ok &= A::div_safe(yn[k], rn[k]);
   }
   if (ok) {
 #pragma unroll

@@ -1,20 +1,26 @@
-// mt_pipe.cuh -- persistent, TMA-pipelined step kernel for batched roads.
+// mt_pipe.cuh -- persistent, warp-specialised, TMA-pipelined step kernel for
+// batched roads (the hot kernel of the engine).
 //
-// One CTA per SM slot (grid = min(#tiles, SMs x CTAs/SM)) walks over tiles of
-// consecutive roads.  A tile (<= 16 KB of [rho | v] rows, contiguous in HBM)
-// is fetched with ONE bulk asynchronous copy (cp.async.bulk, the 1-D TMA path)
-// into a ring of STAGES shared-memory buffers, each guarded by an mbarrier;
-// the finished tile is staged in shared memory and written back with one bulk
-// store.  Loads for the next STAGES-1 tiles and the stores of the previous
-// tiles are in flight while the CTA computes, so HBM latency is decoupled
-// from the FP64 work instead of being exposed once per CTA.
+// Grid: min(#tiles, SMs x 2) CTAs, each walking over tiles of consecutive
+// roads.  A tile (<= 16 KB of [rho | v] rows, contiguous in HBM) is fetched
+// with ONE bulk asynchronous copy (cp.async.bulk, the 1-D TMA path) into a
+// ring of PIPE_STAGES shared-memory buffers; the finished tile is staged in one
+// of PIPE_OUT shared-memory buffers and written back with one bulk store.
 //
-// Per tile: wait(full[s]) -> every thread reads its 16-byte vectors of rho and
-// v from shared memory and derives the per-cell flux ingredients -> edge
-// values go through a small exchange array (__syncthreads A) -> update,
-// boundary rule, (rho,y)->(rho,v), results to the output stage ->
-// fence.proxy.async + __syncthreads B -> thread 0 issues the bulk store and
-// re-arms stage s with the load of tile i+STAGES.
+// Roles inside a CTA (NC consumer threads + one producer warp):
+//   producer (1 thread): re-arms input stages (cp.async.bulk + expect_tx) as
+//     soon as the consumers release them, issues the bulk store of a finished
+//     tile, and hands output stages back once the store has read them.
+//   consumers: wait(full[s]) -> read their cells from shared memory, derive
+//     the per-cell flux ingredients, swap three edge values through a small
+//     exchange array (one named barrier among the consumers), release the
+//     input stage, wait(out_free[o]), finish the update and write the result
+//     to the output stage, then arrive on out_full[o] WITHOUT blocking and
+//     move on to the next tile.
+// Loads for the next PIPE_STAGES-1 tiles and the stores of previous tiles are
+// in flight while the consumers compute, so HBM latency is decoupled from the
+// FP64 work; all hand-offs are mbarriers (no CTA-wide __syncthreads in the
+// steady state).
 #pragma once
 #include <stdint.h>
 #include "mtraffic.h"
@@ -23,10 +29,16 @@
 
 namespace mt {
 
-constexpr int PIPE_BLOCK = 512;
-constexpr int PIPE_STAGES = 4;
+constexpr int PIPE_BLOCK = 512;                   // consumer threads at U = 1
 constexpr int PIPE_OUT = 2;
-constexpr int PIPE_TILE_BYTES = PIPE_BLOCK * 32;  // 16 KB: one 16 B vector of rho and of v per thread
+constexpr int PIPE_TILE_BYTES = PIPE_BLOCK * 32;  // 16 KB
+constexpr int PIPE_MAX_EPC = 64;                  // roads per tile (cap)
+// input stages: as many as fit next to the exchange arrays with two CTAs per SM
+template <typename T, int U> struct PipeCfg {
+  static constexpr int NC = PIPE_BLOCK / U;                     // consumer threads
+  static constexpr int XCH = NC + PIPE_MAX_EPC + 8;             // one pad slot per road
+  static constexpr int STAGES = (sizeof(T) == 8 && U == 1) ? 3 : 4;
+};
 
 // ---- PTX wrappers -----------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -41,12 +53,14 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
@@ -55,23 +69,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "@P1 bra DONE;\n"
       "bra LAB_WAIT;\n"
       "DONE:\n"
-      "}" ::"r"(smem_u32(bar)),
+      "}" ::"r"(bar),
       "r"(parity)
       : "memory");
 }
 // global -> shared, completion counted in bytes on an mbarrier
-__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes,
-                                          uint64_t* bar) {
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src_gmem, uint32_t bytes,
+                                          uint32_t bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-          "r"(smem_u32(dst_smem)),
-      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+          "r"(dst_smem),
+      "l"(src_gmem), "r"(bytes), "r"(bar)
       : "memory");
 }
 // shared -> global, tracked by the per-thread bulk async-group
-__device__ __forceinline__ void bulk_store(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+__device__ __forceinline__ void bulk_store(void* dst_gmem, uint32_t src_smem, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
-               "r"(smem_u32(src_smem)), "r"(bytes)
+               "r"(src_smem), "r"(bytes)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() {
@@ -80,20 +94,49 @@ __device__ __forceinline__ void bulk_commit() {
 template <int N> __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
+// barrier among the consumer threads only (id 1; id 0 is __syncthreads)
+__device__ __forceinline__ void consumer_sync(int nc) {
+  asm volatile("bar.sync 1, %0;" ::"r"(nc) : "memory");
+}
+// 16-byte shared-memory accesses on 32-bit shared addresses
+__device__ __forceinline__ void lds16(uint32_t addr, double (&a)[2]) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a[0]), "=d"(a[1]) : "r"(addr));
+}
+__device__ __forceinline__ void lds16(uint32_t addr, float (&a)[4]) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void sts16(uint32_t addr, const double (&a)[2]) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a[0]), "d"(a[1]) : "memory");
+}
+__device__ __forceinline__ void sts16(uint32_t addr, const float (&a)[4]) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a[0]), "f"(a[1]),
+               "f"(a[2]), "f"(a[3])
+               : "memory");
+}
 
 // ---- shared-memory layout ---------------------------------------------------
-constexpr int PIPE_MAX_EPC = 64;                       // roads per tile (cap)
-constexpr int PIPE_XCH = PIPE_BLOCK + PIPE_MAX_EPC + 8;  // one pad slot per road in the tile
-
-template <typename T> struct PipeSmem {
-  alignas(128) unsigned char in[PIPE_STAGES][PIPE_TILE_BYTES];
+template <typename T, int U> struct PipeSmem {
+  static constexpr int STAGES = PipeCfg<T, U>::STAGES;
+  static constexpr int XCH = PipeCfg<T, U>::XCH;
+  alignas(128) unsigned char in[STAGES][PIPE_TILE_BYTES];
   alignas(128) unsigned char out[PIPE_OUT][PIPE_TILE_BYTES];
-  T xS[PIPE_XCH], xD[PIPE_XCH], xR[PIPE_XCH];  // edge exchange
+  // edge exchange, double-buffered by tile parity: the consumers meet at one
+  // barrier per tile, so a fast warp may already write tile i+1's edges while
+  // a slow one still reads tile i's
+  T xS[2][XCH], xD[2][XCH], xR[2][XCH];
   T s_num[PIPE_BLOCK / 32], s_den[PIPE_BLOCK / 32];
-  alignas(8) uint64_t full[PIPE_STAGES];
+  alignas(8) uint64_t full[STAGES];         // producer -> consumers: tile landed
+  uint64_t empty[STAGES];                   // consumers -> producer: stage read
+  uint64_t out_full[PIPE_OUT];              // consumers -> producer: result staged
+  uint64_t out_free[PIPE_OUT];              // producer -> consumers: store drained
 };
-
-static_assert(sizeof(PipeSmem<double>) <= 113 * 1024, "two CTAs per SM must fit in 227 KB");
+// two CTAs per SM: 2 x (smem + 1 KB reserved) <= 228 KB
+static_assert(sizeof(PipeSmem<double, 1>) <= 113 * 1024, "f64 U=1 does not fit twice per SM");
+static_assert(sizeof(PipeSmem<double, 2>) <= 113 * 1024, "f64 U=2 does not fit twice per SM");
+static_assert(sizeof(PipeSmem<float, 1>) <= 113 * 1024, "f32 U=1 does not fit twice per SM");
+static_assert(sizeof(PipeSmem<float, 2>) <= 113 * 1024, "f32 U=2 does not fit twice per SM");
 
 template <typename T> struct PipeArgs {
   const T* in;
@@ -102,13 +145,13 @@ template <typename T> struct PipeArgs {
   const int* flags;
   const T* action;
   T* reward;   // nullptr: no reward reduction
-  long long B;
+  int B;
   int N;
   int nthr;    // threads that own cells in one road: N / CPT
   int tpe;     // threads per road (padded)
   int epc;     // roads per tile
   int n_tiles;
-  int block;   // threads per CTA
+  int nc;      // consumer threads per CTA (the CTA has nc + 32 threads)
   BcArgs<T> bc;
   T step;
   UniformC<T> u;  // used by the UNIFORM instantiations
@@ -118,53 +161,96 @@ template <typename T> struct PipeArgs {
 // LAM_RUNTIME.  UNIFORM: every road shares the scalar parameters in a.u.
 // U: 16-byte vectors (of each field) per thread; a thread owns U*V cells.
 template <typename T, int MODEL, bool FAST, int LAMK, bool UNIFORM, int U>
-__global__ void __launch_bounds__(PIPE_BLOCK / U, 2) step_pipe_kernel(const PipeArgs<T> a) {
+__global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) step_pipe_kernel(const PipeArgs<T> a) {
   constexpr int V = Vec<T>::N;
   constexpr int CPT = U * V;
   constexpr bool ARZ = (MODEL == 1);
-  using VT = typename Vec<T>::type;
+  constexpr int PIPE_STAGES = PipeCfg<T, U>::STAGES;
+  constexpr int PIPE_XCH = PipeCfg<T, U>::XCH;
   using A = Ar<T, FAST>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  PipeSmem<T>& sm = *reinterpret_cast<PipeSmem<T>*>(smem_raw);
+  PipeSmem<T, U>& sm = *reinterpret_cast<PipeSmem<T, U>*>(smem_raw);
 
   const int t = threadIdx.x;
+  const int NC = a.nc;
   const int N = a.N;
   const uint32_t row_bytes = 2u * (uint32_t)N * (uint32_t)sizeof(T);
+  const uint32_t tile_bytes = (uint32_t)a.epc * row_bytes;
   const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const bool want_reward = a.reward != nullptr;
+  const int last_tile = a.n_tiles - 1;
+  const int last_envs = a.B - last_tile * a.epc;  // roads in the (ragged) last tile
 
-  auto tile_envs = [&](int tile) -> int {
-    const long long left = a.B - (long long)tile * a.epc;
-    return left < a.epc ? (int)left : a.epc;
-  };
-  auto issue_load = [&](int i) {  // thread 0 only
-    const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-    const int s = i % PIPE_STAGES;
-    const uint32_t bytes = (uint32_t)tile_envs(tile) * row_bytes;
-    mbar_expect_tx(&sm.full[s], bytes);
-    bulk_load(sm.in[s], reinterpret_cast<const unsigned char*>(a.in) +
-                            (size_t)tile * a.epc * row_bytes, bytes, &sm.full[s]);
-  };
+  const uint32_t in0 = smem_u32(sm.in[0]), out0 = smem_u32(sm.out[0]);
+  const uint32_t full0 = smem_u32(&sm.full[0]), empty0 = smem_u32(&sm.empty[0]);
+  const uint32_t ofull0 = smem_u32(&sm.out_full[0]), ofree0 = smem_u32(&sm.out_free[0]);
 
   // pad slots of the exchange arrays stay zero for the kernel's life: they
   // feed the (discarded) left-face flux of each road's first cell
-  for (int i = t; i < PIPE_XCH; i += blockDim.x) { sm.xD[i] = T(0); sm.xR[i] = T(0); }
+  for (int i = t; i < 2 * PIPE_XCH; i += blockDim.x) { (&sm.xD[0][0])[i] = T(0); (&sm.xR[0][0])[i] = T(0); }
   if (t == 0) {
-    for (int s = 0; s < PIPE_STAGES; ++s) mbar_init(&sm.full[s], 1);
+    for (int s = 0; s < PIPE_STAGES; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], (uint32_t)(NC >> 5));
+    }
+    for (int o = 0; o < PIPE_OUT; ++o) {
+      mbar_init(&sm.out_full[o], (uint32_t)(NC >> 5));
+      mbar_init(&sm.out_free[o], 1);
+    }
     fence_mbar_init();
   }
   __syncthreads();
-  if (t == 0) {
-    const int pre = n_my < PIPE_STAGES ? n_my : PIPE_STAGES;
-    for (int i = 0; i < pre; ++i) issue_load(i);
+
+  // ======================= producer warp ===================================
+  if (t >= NC) {
+    if (t == NC) {
+      const unsigned char* gin = reinterpret_cast<const unsigned char*>(a.in);
+      unsigned char* gout = reinterpret_cast<unsigned char*>(a.out);
+      auto bytes_of = [&](int tile) -> uint32_t {
+        return tile == last_tile ? (uint32_t)last_envs * row_bytes : tile_bytes;
+      };
+      auto issue_load = [&](int i) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int s = i % PIPE_STAGES;
+        const uint32_t bytes = bytes_of(tile);
+        mbar_expect_tx(full0 + 8 * s, bytes);
+        bulk_load(in0 + (uint32_t)s * PIPE_TILE_BYTES, gin + (size_t)tile * tile_bytes, bytes,
+                  full0 + 8 * s);
+      };
+      const int pre = n_my < PIPE_STAGES ? n_my : PIPE_STAGES;
+      for (int i = 0; i < pre; ++i) issue_load(i);
+      for (int i = 0; i < n_my; ++i) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int s = i % PIPE_STAGES, o = i % PIPE_OUT;
+        if (i + PIPE_STAGES < n_my) {  // refill stage s once the consumers have read tile i
+          mbar_wait(empty0 + 8 * s, (uint32_t)((i / PIPE_STAGES) & 1));
+          issue_load(i + PIPE_STAGES);
+        }
+        mbar_wait(ofull0 + 8 * o, (uint32_t)((i / PIPE_OUT) & 1));
+        bulk_store(gout + (size_t)tile * tile_bytes, out0 + (uint32_t)o * PIPE_TILE_BYTES,
+                   bytes_of(tile));
+        bulk_commit();
+        // all but the newest PIPE_OUT-1 stores have finished reading shared memory
+        bulk_wait_read<PIPE_OUT - 1>();
+        if (i >= PIPE_OUT - 1) mbar_arrive(ofree0 + 8 * ((i - (PIPE_OUT - 1)) % PIPE_OUT));
+      }
+      bulk_wait_read<0>();  // shared memory must outlive the last bulk store
+    }
+    return;
   }
 
+  // ======================= consumers =======================================
   // thread -> (road in tile, position in road); fixed for the kernel's life
   const int el = t / a.tpe;
   const int pos = t - el * a.tpe;
   const bool row_first = (pos == 0), row_last = (pos == a.nthr - 1);
-  const size_t row_off = (size_t)el * 2 * N;
+  const bool owns_cells = (pos < a.nthr) && (el < a.epc);
   const int xi = t + el;  // exchange slot (one pad slot per road)
+  const bool lane0 = (t & 31) == 0;
+  const bool want_reward = a.reward != nullptr;
+  // byte offsets of my first rho vector inside a stage, and of the v block
+  const uint32_t my_off = (uint32_t)el * row_bytes + (uint32_t)pos * (U * 16);
+  const uint32_t v_off = (uint32_t)N * (uint32_t)sizeof(T);
+  const uint32_t row0_off = (uint32_t)el * row_bytes;  // my road's first byte
 
   EnvC<T> e;
   if (UNIFORM) {
@@ -172,13 +258,13 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U, 2) step_pipe_kernel(const Pipe
     if (ARZ) e.qc = A::mul(e.rho_crit, A::mul(e.v_max, e.g_crit));
   }
 
+  int s = 0, o = 0;
+  uint32_t ph_in = 0, ph_out = 0;
   for (int i = 0; i < n_my; ++i) {
     const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-    const int s = i % PIPE_STAGES;
-    const int o = i % PIPE_OUT;
-    const int envs_here = tile_envs(tile);
-    const long long env = (long long)tile * a.epc + el;
-    const bool active = (el < envs_here) && (pos < a.nthr);
+    const int envs_here = tile == last_tile ? last_envs : a.epc;
+    const int env = tile * a.epc + el;
+    const bool active = owns_cells && (el < envs_here);
 
     if (active && (!UNIFORM || a.action != nullptr)) {
       // per-road constants (and/or this step's speed limit): issued before the
@@ -188,72 +274,73 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U, 2) step_pipe_kernel(const Pipe
       if (ARZ) e.qc = A::mul(e.rho_crit, A::mul(e.v_max, e.g_crit));
     }
 
-    mbar_wait(&sm.full[s], (uint32_t)((i / PIPE_STAGES) & 1));
+    mbar_wait(full0 + 8 * s, ph_in);
 
     T rho[CPT], v[CPT], y[CPT], r[CPT], D[CPT], S[CPT];
     T loop_a = 0, loop_b = 0;  // old boundary-source cells for the LOOP rule
+    T* const xS = sm.xS[i & 1];
+    T* const xD = sm.xD[i & 1];
+    T* const xR = sm.xR[i & 1];
     if (active) {
-      const T* row = reinterpret_cast<const T*>(sm.in[s]) + row_off;
+      const uint32_t src = in0 + (uint32_t)s * PIPE_TILE_BYTES + my_off;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         T tmp[V];
-        unpack(reinterpret_cast<const VT*>(row)[pos * U + u], tmp);
+        lds16(src + 16 * u, tmp);
 #pragma unroll
         for (int k = 0; k < V; ++k) rho[u * V + k] = tmp[k];
         if (ARZ) {
-          unpack(reinterpret_cast<const VT*>(row + N)[pos * U + u], tmp);
+          lds16(src + v_off + 16 * u, tmp);
 #pragma unroll
           for (int k = 0; k < V; ++k) v[u * V + k] = tmp[k];
         }
       }
+      if (row_first && a.bc.bc_l == MT_BC_LOOP) {
+        const T* row = reinterpret_cast<const T*>(sm.in[s] + row0_off);
+        if (ARZ) { loop_a = row[N - 1]; loop_b = row[2 * N - 1]; }
+        else { loop_a = row[N - 2]; loop_b = row[N - 1]; }
+      }
       if (ARZ) {
         arz_pass1<T, FAST, LAMK, CPT>(e, rho, v, y, r, D, S);
-        sm.xR[xi + 1] = r[CPT - 1];
-        if (row_first) { loop_a = row[N - 1]; loop_b = row[2 * N - 1]; }
+        xR[xi + 1] = r[CPT - 1];
       } else {
         lwr_pass1<T, FAST, LAMK, CPT>(e, rho, D, S);
-        if (row_first) { loop_a = row[N - 2]; loop_b = row[N - 1]; }
       }
-      sm.xS[xi] = S[0];
-      sm.xD[xi + 1] = D[CPT - 1];
-      if (row_last) sm.xS[xi + 1] = S[CPT - 1];  // arz.py:405 / lwr.py:294
+      xS[xi] = S[0];
+      xD[xi + 1] = D[CPT - 1];
+      if (row_last) xS[xi + 1] = S[CPT - 1];  // arz.py:405 / lwr.py:294
     }
-    // the output stage about to be overwritten must have been drained by the
-    // bulk store issued PIPE_OUT tiles ago
-    if (t == 0) bulk_wait_read<PIPE_OUT - 1>();
-    __syncthreads();  // A
+    consumer_sync(NC);                               // exchange visible; stage s fully read
+    if (lane0) mbar_arrive(empty0 + 8 * s);          // release the input stage
+    mbar_wait(ofree0 + 8 * o, ph_out ^ 1);           // output stage drained by its last store
 
     T num = 0, den = 0;
     if (active) {
       T rn[CPT], vn[CPT];
       if (ARZ)
         arz_pass2<T, FAST, LAMK, CPT>(e, a.bc, row_first, row_last, rho, v, y, r, D, S,
-                                      sm.xS[xi + 1], sm.xD[xi], sm.xR[xi], loop_a, loop_b, rn, vn);
+                                      xS[xi + 1], xD[xi], xR[xi], loop_a, loop_b, rn, vn);
       else
-        lwr_pass2<T, FAST, LAMK, CPT>(e, a.bc, row_first, row_last, rho, D, S, sm.xS[xi + 1],
-                                      sm.xD[xi], loop_a, loop_b, rn, vn);
+        lwr_pass2<T, FAST, LAMK, CPT>(e, a.bc, row_first, row_last, rho, D, S, xS[xi + 1],
+                                      xD[xi], loop_a, loop_b, rn, vn);
       if (want_reward) {
 #pragma unroll
         for (int k = 0; k < CPT; ++k) { num += rn[k] * vn[k]; den += rn[k]; }
       }
-      T* orow = reinterpret_cast<T*>(sm.out[o]) + row_off;
+      const uint32_t dst = out0 + (uint32_t)o * PIPE_TILE_BYTES + my_off;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         T tr[V], tv[V];
 #pragma unroll
         for (int k = 0; k < V; ++k) { tr[k] = rn[u * V + k]; tv[k] = vn[u * V + k]; }
-        reinterpret_cast<VT*>(orow)[pos * U + u] = pack(tr);
-        reinterpret_cast<VT*>(orow + N)[pos * U + u] = pack(tv);
+        sts16(dst + 16 * u, tr);
+        sts16(dst + v_off + 16 * u, tv);
       }
     }
     fence_proxy_async_smem();  // my generic-proxy writes -> visible to the bulk engine
-    __syncthreads();           // B
-    if (t == 0) {
-      bulk_store(reinterpret_cast<unsigned char*>(a.out) + (size_t)tile * a.epc * row_bytes,
-                 sm.out[o], (uint32_t)envs_here * row_bytes);
-      bulk_commit();
-      if (i + PIPE_STAGES < n_my) issue_load(i + PIPE_STAGES);
-    }
+    __syncwarp();
+    if (lane0) mbar_arrive(ofull0 + 8 * o);          // non-blocking hand-off to the producer
+
     if (want_reward) {
       // per-road sum(rho v)/sum(rho) in a fixed order
       const unsigned full = 0xffffffffu;
@@ -268,8 +355,8 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U, 2) step_pipe_kernel(const Pipe
           num += __shfl_xor_sync(full, num, off);
           den += __shfl_xor_sync(full, den, off);
         }
-        if ((t & 31) == 0) { sm.s_num[t >> 5] = num; sm.s_den[t >> 5] = den; }
-        __syncthreads();
+        if (lane0) { sm.s_num[t >> 5] = num; sm.s_den[t >> 5] = den; }
+        consumer_sync(NC);
         if (active && row_first) {
           const int w0 = t >> 5, nw = a.tpe >> 5;
           T n = sm.s_num[w0], d = sm.s_den[w0];
@@ -278,8 +365,9 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U, 2) step_pipe_kernel(const Pipe
         }
       }
     }
+    if (++s == PIPE_STAGES) { s = 0; ph_in ^= 1; }
+    if (++o == PIPE_OUT) { o = 0; ph_out ^= 1; }
   }
-  if (t == 0) bulk_wait_read<0>();  // shared memory must outlive the last bulk store
 }
 
 }  // namespace mt

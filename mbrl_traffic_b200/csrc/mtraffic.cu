@@ -188,13 +188,13 @@ Geometry plan(long long B, int N, int V, bool aligned) {
 template <typename T, int MODEL, bool FAST, int LAMK, bool UNIFORM, int U>
 int launch_pipe(const PipeArgs<T>& pa, int grid, cudaStream_t stream) {
   static bool configured = false;  // per instantiation; the attribute is per function
-  const size_t smem = sizeof(PipeSmem<T>);
+  const size_t smem = sizeof(PipeSmem<T, U>);
   if (!configured) {
     CUDA_TRY(cudaFuncSetAttribute(step_pipe_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  step_pipe_kernel<T, MODEL, FAST, LAMK, UNIFORM, U><<<grid, pa.block, smem, stream>>>(pa);
+  step_pipe_kernel<T, MODEL, FAST, LAMK, UNIFORM, U><<<grid, pa.nc + 32, smem, stream>>>(pa);
   return MT_OK;
 }
 
@@ -298,12 +298,13 @@ int step_typed(mt_engine* e, const void* obs_in, const void* action, void* obs_o
     pa.flags = e->flags;
     pa.action = (const T*)action;
     pa.reward = (T*)reward_out;
-    pa.B = B;
+    if (B > 0x7fffffffLL) return fail(MT_EINVAL, "batch too large for one launch");
+    pa.B = (int)B;
     pa.N = N;
     pa.nthr = N / (U * V);
-    pa.block = PIPE_BLOCK / U;
+    pa.nc = PIPE_BLOCK / U;
     pa.tpe = pa.nthr <= 32 ? next_pow2(pa.nthr) : ((pa.nthr + 31) / 32) * 32;
-    pa.epc = pa.block / pa.tpe;
+    pa.epc = pa.nc / pa.tpe;
     if (pa.epc > PIPE_MAX_EPC) pa.epc = PIPE_MAX_EPC;
     const long long n_tiles = (B + pa.epc - 1) / pa.epc;
     if (n_tiles > 0x7fffffffLL) return fail(MT_EINVAL, "batch too large for one launch");
