@@ -91,6 +91,11 @@ __device__ __forceinline__ void bulk_store(void* dst_gmem, uint32_t src_smem, ui
 __device__ __forceinline__ void bulk_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// global -> L2 only: warms the line for a later bulk_load without holding
+// shared memory, so HBM latency is covered beyond what the stage ring can hold
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 template <int N> __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
@@ -152,6 +157,7 @@ template <typename T> struct PipeArgs {
   int epc;     // roads per tile
   int n_tiles;
   int nc;      // consumer threads per CTA (the CTA has nc + 32 threads)
+  int l2_ahead;  // tiles prefetched into L2 beyond the shared-memory ring
   BcArgs<T> bc;
   T step;
   UniformC<T> u;  // used by the UNIFORM instantiations
@@ -216,11 +222,18 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) step_pipe_kernel(const
         bulk_load(in0 + (uint32_t)s * PIPE_TILE_BYTES, gin + (size_t)tile * tile_bytes, bytes,
                   full0 + 8 * s);
       };
+      auto prefetch = [&](int i) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        bulk_prefetch_l2(gin + (size_t)tile * tile_bytes, bytes_of(tile));
+      };
       const int pre = n_my < PIPE_STAGES ? n_my : PIPE_STAGES;
       for (int i = 0; i < pre; ++i) issue_load(i);
+      const int ahead = a.l2_ahead;
+      for (int i = PIPE_STAGES; i < PIPE_STAGES + ahead && i < n_my; ++i) prefetch(i);
       for (int i = 0; i < n_my; ++i) {
         const int tile = (int)blockIdx.x + i * (int)gridDim.x;
         const int s = i % PIPE_STAGES, o = i % PIPE_OUT;
+        if (ahead > 0 && i + PIPE_STAGES + ahead < n_my) prefetch(i + PIPE_STAGES + ahead);
         if (i + PIPE_STAGES < n_my) {  // refill stage s once the consumers have read tile i
           mbar_wait(empty0 + 8 * s, (uint32_t)((i / PIPE_STAGES) & 1));
           issue_load(i + PIPE_STAGES);

@@ -150,7 +150,11 @@ struct mt_engine {
   cudaEvent_t params_ready = nullptr;
   cudaStream_t params_stream = nullptr;
   bool params_pending = false;
-  // host staging
+  // host staging: chunks of roads are pipelined over these streams so that the
+  // upload of one chunk overlaps the compute and the download of others
+  static constexpr int HOST_STREAMS = 3;
+  cudaStream_t hs[HOST_STREAMS] = {nullptr, nullptr, nullptr};
+  cudaEvent_t action_ready = nullptr;
   cudaStream_t stream = nullptr;
   void *d_a = nullptr, *d_b = nullptr, *d_action = nullptr, *d_reward = nullptr;
 };
@@ -200,6 +204,8 @@ int launch_pipe(const PipeArgs<T>& pa, int grid, cudaStream_t stream) {
 
 template <typename T, int MODEL, bool FAST, int U>
 int launch_pipe_lam(const PipeArgs<T>& pa, int grid, bool uniform, int lamk, cudaStream_t s) {
+  if (uniform && lamk == LAM_ONE && pa.u.rho_max == T(1))
+    return launch_pipe<T, MODEL, FAST, LAM_ONE_RM1, true, U>(pa, grid, s);
   if (uniform && lamk == LAM_ONE) return launch_pipe<T, MODEL, FAST, LAM_ONE, true, U>(pa, grid, s);
   if (uniform && lamk == LAM_TWO) return launch_pipe<T, MODEL, FAST, LAM_TWO, true, U>(pa, grid, s);
   if (uniform && lamk == LAM_HALF) return launch_pipe<T, MODEL, FAST, LAM_HALF, true, U>(pa, grid, s);
@@ -254,6 +260,17 @@ void make_uniform(UniformC<T>& u, int& lamk, int model, const mt_params& p) {
             (host_is_pow2((double)c) ? FLAG_C_POW2 : 0);
 }
 
+int pipe_l2_ahead() {
+  static int v = -1;
+  if (v < 0) {
+    const char* s = getenv("MT_PIPE_L2_AHEAD");
+    v = s ? atoi(s) : 2;  // measured best on B200
+    if (v < 0) v = 0;
+    if (v > 64) v = 64;
+  }
+  return v;
+}
+
 // cells per thread of the pipelined kernel: U 16-byte vectors of each field
 int pipe_vectors_per_thread() {
   static int u = -1;
@@ -264,13 +281,22 @@ int pipe_vectors_per_thread() {
   return u;
 }
 
+// Steps roads [env0, env0 + n_env) of the batch; all pointers address the
+// whole batch (road 0) and are offset here.
 template <typename T>
-int step_typed(mt_engine* e, const void* obs_in, const void* action, void* obs_out,
-               void* reward_out, cudaStream_t stream) {
+int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs_out_,
+               void* reward_out_, long long env0, long long n_env, cudaStream_t stream) {
   constexpr int V = Vec<T>::N;
   const mt_params& p = e->params;
-  const long long B = e->cfg.n_envs;
+  const long long B = n_env;
   const int N = (int)e->cfg.n_cells;
+  const T* obs_in = (const T*)obs_in_ + env0 * 2 * N;
+  T* obs_out = (T*)obs_out_ + env0 * 2 * N;
+  const T* action = action_ ? (const T*)action_ + env0 : nullptr;
+  T* reward_out = reward_out_ ? (T*)reward_out_ + env0 : nullptr;
+  const T* table = (const T*)e->table + env0 * TBL_STRIDE;
+  const int* flags = e->flags + env0;
+  T* partial = e->partial ? (T*)e->partial + env0 * e->max_tiles * 2 : nullptr;
   const bool aligned = (((uintptr_t)obs_in | (uintptr_t)obs_out) & 15u) == 0;
   const Geometry g = plan(B, N, V, aligned);
   const bool fast = FastAllowed<T>::value && (p.flags & MT_FLAG_FAST_MATH) != 0;
@@ -292,17 +318,18 @@ int step_typed(mt_engine* e, const void* obs_in, const void* action, void* obs_o
     if (U == 0) U = (sizeof(T) == 8) ? 2 : 1;
     if (N % (U * V) != 0 || N < 2 * U * V) U = 1;
     PipeArgs<T> pa;
-    pa.in = (const T*)obs_in;
-    pa.out = (T*)obs_out;
-    pa.table = (const T*)e->table;
-    pa.flags = e->flags;
-    pa.action = (const T*)action;
-    pa.reward = (T*)reward_out;
+    pa.in = obs_in;
+    pa.out = obs_out;
+    pa.table = table;
+    pa.flags = flags;
+    pa.action = action;
+    pa.reward = reward_out;
     if (B > 0x7fffffffLL) return fail(MT_EINVAL, "batch too large for one launch");
     pa.B = (int)B;
     pa.N = N;
     pa.nthr = N / (U * V);
     pa.nc = PIPE_BLOCK / U;
+    pa.l2_ahead = pipe_l2_ahead();
     pa.tpe = pa.nthr <= 32 ? next_pow2(pa.nthr) : ((pa.nthr + 31) / 32) * 32;
     pa.epc = pa.nc / pa.tpe;
     if (pa.epc > PIPE_MAX_EPC) pa.epc = PIPE_MAX_EPC;
@@ -328,13 +355,13 @@ int step_typed(mt_engine* e, const void* obs_in, const void* action, void* obs_o
   }
 
   StepArgs<T> a;
-  a.in = (const T*)obs_in;
-  a.out = (T*)obs_out;
-  a.table = (const T*)e->table;
-  a.flags = e->flags;
-  a.action = (const T*)action;
-  a.reward = (T*)reward_out;
-  a.partial = (T*)e->partial;
+  a.in = obs_in;
+  a.out = obs_out;
+  a.table = table;
+  a.flags = flags;
+  a.action = action;
+  a.reward = reward_out;
+  a.partial = partial;
   a.B = B;
   a.N = N;
   a.nvec = g.nvec;
@@ -364,7 +391,7 @@ int step_typed(mt_engine* e, const void* obs_in, const void* action, void* obs_o
     e->launches++;
     if (rew && g.tiles > 1) {
       reward_finalize_kernel<T><<<(unsigned)((B + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
-          (const T*)e->partial, (T*)reward_out, B, g.tiles);
+          (const T*)partial, reward_out, B, g.tiles);
       e->launches++;
     }
   } else {
@@ -382,12 +409,21 @@ int step_typed(mt_engine* e, const void* obs_in, const void* action, void* obs_o
     e->launches++;
     if (rew) {
       reward_rows_kernel<T><<<(unsigned)((B + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
-          (const T*)obs_out, (T*)reward_out, B, N);
+          (const T*)obs_out, reward_out, B, N);
       e->launches++;
     }
   }
   CUDA_TRY(cudaGetLastError());
   return MT_OK;
+}
+
+int step_range(mt_engine* e, const void* obs_in, const void* action, void* obs_out,
+               void* reward_out, long long env0, long long n_env, cudaStream_t stream) {
+  if (e->cfg.model == MT_MODEL_NONLOCAL)
+    return fail(MT_EINVAL, "the non-local model has no step kernel yet");
+  if (e->cfg.dtype == MT_F64)
+    return step_typed<double>(e, obs_in, action, obs_out, reward_out, env0, n_env, stream);
+  return step_typed<float>(e, obs_in, action, obs_out, reward_out, env0, n_env, stream);
 }
 
 int step_any(mt_engine* e, const void* obs_in, const void* action, void* obs_out,
@@ -396,10 +432,7 @@ int step_any(mt_engine* e, const void* obs_in, const void* action, void* obs_out
     if (stream != e->params_stream) CUDA_TRY(cudaStreamWaitEvent(stream, e->params_ready, 0));
     e->params_pending = false;
   }
-  if (e->cfg.model == MT_MODEL_NONLOCAL)
-    return fail(MT_EINVAL, "the non-local model has no step kernel yet");
-  if (e->cfg.dtype == MT_F64) return step_typed<double>(e, obs_in, action, obs_out, reward_out, stream);
-  return step_typed<float>(e, obs_in, action, obs_out, reward_out, stream);
+  return step_range(e, obs_in, action, obs_out, reward_out, 0, e->cfg.n_envs, stream);
 }
 
 bool valid_bc(int bc) { return bc >= MT_BC_LOOP && bc <= MT_BC_HALO; }
@@ -448,7 +481,10 @@ int mt_create(const mt_config* cfg, mt_engine** out) {
   if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
   if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->params_ready, cudaEventDisableTiming);
   if (err == cudaSuccess && cfg->host_staging) {
-    err = cudaMalloc(&e->d_a, B * 2 * N * e->elt);
+    for (int i = 0; i < mt_engine::HOST_STREAMS && err == cudaSuccess; ++i)
+      err = cudaStreamCreateWithFlags(&e->hs[i], cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->action_ready, cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaMalloc(&e->d_a, B * 2 * N * e->elt);
     if (err == cudaSuccess) err = cudaMalloc(&e->d_b, B * 2 * N * e->elt);
     if (err == cudaSuccess) err = cudaMalloc(&e->d_action, B * e->elt);
     if (err == cudaSuccess) err = cudaMalloc(&e->d_reward, B * e->elt);
@@ -474,6 +510,9 @@ void mt_destroy(mt_engine* e) {
   cudaFree(e->d_action);
   cudaFree(e->d_reward);
   if (e->stream) cudaStreamDestroy(e->stream);
+  for (int i = 0; i < mt_engine::HOST_STREAMS; ++i)
+    if (e->hs[i]) cudaStreamDestroy(e->hs[i]);
+  if (e->action_ready) cudaEventDestroy(e->action_ready);
   if (e->params_ready) cudaEventDestroy(e->params_ready);
   delete e;
 }
@@ -563,24 +602,53 @@ int mt_step_host(mt_engine* e, const void* obs_in_host, const void* action_host,
   if (!e->d_a) return fail(MT_ESTATE, "mt_step_host: engine created without host_staging");
   if (n_steps < 1) return fail(MT_EINVAL, "mt_step_host: n_steps must be >= 1");
   CUDA_TRY(cudaSetDevice(e->cfg.device));
-  const size_t B = (size_t)e->cfg.n_envs, N = (size_t)e->cfg.n_cells;
-  const size_t obs_bytes = B * 2 * N * e->elt, env_bytes = B * e->elt;
-  cudaStream_t s = e->stream;
-  CUDA_TRY(cudaMemcpyAsync(e->d_a, obs_in_host, obs_bytes, cudaMemcpyHostToDevice, s));
-  if (action_host)
-    CUDA_TRY(cudaMemcpyAsync(e->d_action, action_host, env_bytes, cudaMemcpyHostToDevice, s));
-  void* cur = e->d_a;
-  void* nxt = e->d_b;
-  for (int i = 0; i < n_steps; ++i) {
-    void* rew = (reward_out_host && i == n_steps - 1) ? e->d_reward : nullptr;
-    const int rc = step_any(e, cur, action_host ? e->d_action : nullptr, nxt, rew, s);
-    if (rc != MT_OK) return rc;
-    void* tmp = cur; cur = nxt; nxt = tmp;
+  const long long B = e->cfg.n_envs;
+  const size_t N = (size_t)e->cfg.n_cells;
+  const size_t row_bytes = 2 * N * e->elt;
+  constexpr int NS = mt_engine::HOST_STREAMS;
+  // Roads are independent, so the batch is cut into chunks that flow through
+  // upload -> n_steps kernels -> download on NS streams: PCIe carries both
+  // directions at once and the kernels hide behind the copies.
+  long long n_chunks = (B * (long long)row_bytes) / (8u << 20);  // ~8 MB per chunk
+  if (n_chunks < 1) n_chunks = 1;
+  if (n_chunks > 16) n_chunks = 16;
+  if (n_chunks > B) n_chunks = B;
+  const long long per = (B + n_chunks - 1) / n_chunks;
+  for (int i = 0; i < NS; ++i) CUDA_TRY(cudaStreamWaitEvent(e->hs[i], e->params_ready, 0));
+  e->params_pending = false;
+  if (action_host) {
+    CUDA_TRY(cudaMemcpyAsync(e->d_action, action_host, (size_t)B * e->elt,
+                             cudaMemcpyHostToDevice, e->hs[0]));
+    CUDA_TRY(cudaEventRecord(e->action_ready, e->hs[0]));
+    for (int i = 1; i < NS; ++i) CUDA_TRY(cudaStreamWaitEvent(e->hs[i], e->action_ready, 0));
   }
-  CUDA_TRY(cudaMemcpyAsync(obs_out_host, cur, obs_bytes, cudaMemcpyDeviceToHost, s));
-  if (reward_out_host)
-    CUDA_TRY(cudaMemcpyAsync(reward_out_host, e->d_reward, env_bytes, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
+  const bool odd = (n_steps & 1) != 0;
+  char* result = (char*)(odd ? e->d_b : e->d_a);
+  for (long long c = 0; c < n_chunks; ++c) {
+    const long long env0 = c * per;
+    const long long n_env = (env0 + per <= B) ? per : B - env0;
+    if (n_env <= 0) break;
+    cudaStream_t s = e->hs[c % NS];
+    const size_t off = (size_t)env0 * row_bytes, bytes = (size_t)n_env * row_bytes;
+    CUDA_TRY(cudaMemcpyAsync((char*)e->d_a + off, (const char*)obs_in_host + off, bytes,
+                             cudaMemcpyHostToDevice, s));
+    void* cur = e->d_a;
+    void* nxt = e->d_b;
+    for (int i = 0; i < n_steps; ++i) {
+      void* rew = (reward_out_host && i == n_steps - 1) ? e->d_reward : nullptr;
+      const int rc = step_range(e, cur, action_host ? e->d_action : nullptr, nxt, rew, env0,
+                                n_env, s);
+      if (rc != MT_OK) return rc;
+      void* tmp = cur; cur = nxt; nxt = tmp;
+    }
+    CUDA_TRY(cudaMemcpyAsync((char*)obs_out_host + off, result + off, bytes,
+                             cudaMemcpyDeviceToHost, s));
+    if (reward_out_host)
+      CUDA_TRY(cudaMemcpyAsync((char*)reward_out_host + (size_t)env0 * e->elt,
+                               (char*)e->d_reward + (size_t)env0 * e->elt,
+                               (size_t)n_env * e->elt, cudaMemcpyDeviceToHost, s));
+  }
+  for (int i = 0; i < NS; ++i) CUDA_TRY(cudaStreamSynchronize(e->hs[i]));
   return MT_OK;
 }
 
