@@ -8,12 +8,14 @@ arguments and ``get_next_obs`` contract) over ``libmtraffic.so``
 from mbrl_traffic_b200.base import Model
 from mbrl_traffic_b200.lwr import LWRModel
 from mbrl_traffic_b200.arz import ARZModel
+from mbrl_traffic_b200.nonlocal_ import NonLocalModel
 from mbrl_traffic_b200.params import LWR_MODEL_PARAMS
 from mbrl_traffic_b200.params import ARZ_MODEL_PARAMS
 from mbrl_traffic_b200.params import NONLOCAL_MODEL_PARAMS
 from mbrl_traffic_b200.engine import Engine, PinnedArray
 
 __all__ = [
-    "Model", "LWRModel", "ARZModel", "Engine", "PinnedArray",
+    "Model", "LWRModel", "ARZModel", "NonLocalModel", "Engine",
+    "PinnedArray",
     "LWR_MODEL_PARAMS", "ARZ_MODEL_PARAMS", "NONLOCAL_MODEL_PARAMS",
 ]

@@ -100,7 +100,7 @@ class FiniteVolumeModel(Model):
             return
         kw = {}
         for name, value in values.items():
-            if isinstance(value, np.ndarray) and name != "gamma":
+            if isinstance(value, np.ndarray):
                 import torch
                 value = torch.as_tensor(
                     np.ascontiguousarray(value, dtype=eng.dtype),

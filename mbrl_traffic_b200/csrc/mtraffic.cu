@@ -14,6 +14,7 @@
 #include "mt_math.cuh"
 #include "mt_pipe.cuh"
 #include "mt_direct.cuh"
+#include "mt_nonlocal.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -281,6 +282,106 @@ int pipe_vectors_per_thread() {
   return u;
 }
 
+
+// ---- non-local model launchers ------------------------------------------------
+template <typename T, bool FAST, int LAMK, bool UNIFORM, int U>
+int launch_nl(const NlArgs<T>& na, int grid, cudaStream_t stream) {
+  static bool configured = false;
+  const size_t smem = sizeof(NlSmem<T>);
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(nonlocal_pipe_kernel<T, FAST, LAMK, UNIFORM, U>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  nonlocal_pipe_kernel<T, FAST, LAMK, UNIFORM, U><<<grid, na.nc + 32, smem, stream>>>(na);
+  return MT_OK;
+}
+
+template <typename T, bool FAST, int U>
+int launch_nl_lam(const NlArgs<T>& na, int grid, bool uniform, int lamk, cudaStream_t s) {
+  if (uniform && lamk == LAM_ONE && na.u.rho_max == T(1))
+    return launch_nl<T, FAST, LAM_ONE_RM1, true, U>(na, grid, s);
+  if (uniform && lamk == LAM_ONE) return launch_nl<T, FAST, LAM_ONE, true, U>(na, grid, s);
+  if (uniform && lamk == LAM_TWO) return launch_nl<T, FAST, LAM_TWO, true, U>(na, grid, s);
+  if (uniform && lamk == LAM_HALF) return launch_nl<T, FAST, LAM_HALF, true, U>(na, grid, s);
+  return launch_nl<T, FAST, LAM_RUNTIME, false, U>(na, grid, s);
+}
+
+template <typename T, int U>
+int launch_nl_fast(const NlArgs<T>& na, int grid, bool fast, bool uniform, int lamk,
+                   cudaStream_t s) {
+  if constexpr (FastAllowed<T>::value) {
+    if (fast) return launch_nl_lam<T, true, U>(na, grid, uniform, lamk, s);
+  }
+  return launch_nl_lam<T, false, U>(na, grid, uniform, lamk, s);
+}
+
+template <typename T>
+int step_nonlocal(mt_engine* e, const T* obs_in, const T* action, T* obs_out, T* reward_out,
+                  const T* table, const int* flags, long long B, bool aligned,
+                  const BcArgs<T>& bc, T step, cudaStream_t stream) {
+  constexpr int V = Vec<T>::N;
+  const mt_params& p = e->params;
+  const int N = (int)e->cfg.n_cells;
+  const int n_eta = p.n_eta;
+  const bool fast = FastAllowed<T>::value && (p.flags & MT_FLAG_FAST_MATH) != 0;
+  if (n_eta > N) return fail(MT_EINVAL, "non-local: n_eta (%d) exceeds n_cells (%d)", n_eta, N);
+  int U = pipe_vectors_per_thread();
+  if (U == 0) U = (sizeof(T) == 8) ? 2 : 1;
+  if (N % (U * V) != 0 || N < 2 * U * V) U = 1;
+  const int CPT = U * V;
+  bool pipe_ok = aligned && (N % CPT == 0) && (N >= 2 * CPT) && !(p.flags & MT_FLAG_NO_PIPELINE) &&
+                 n_eta <= NL_MAX_ETA && B <= 0x7fffffffLL;
+  NlArgs<T> na;
+  if (pipe_ok) {
+    na.nthr = N / CPT;
+    na.nc = PIPE_BLOCK / U;
+    pipe_ok = na.nthr <= na.nc;
+  }
+  if (pipe_ok) {
+    na.tpe = na.nthr <= 32 ? next_pow2(na.nthr) : ((na.nthr + 31) / 32) * 32;
+    na.ve_cols = na.nthr + (n_eta + 1 + CPT - 1) / CPT + 1;
+    na.epc = na.nc / na.tpe;
+    if (na.epc > PIPE_MAX_EPC) na.epc = PIPE_MAX_EPC;
+    const int cap = NlSmem<T>::VE / (CPT * na.ve_cols);   // roads whose V(rho) block fits
+    if (na.epc > cap) na.epc = cap;
+    pipe_ok = na.epc >= 1;
+  }
+  if (pipe_ok) {
+    na.in = obs_in; na.out = obs_out; na.table = table; na.flags = flags;
+    na.action = action; na.reward = reward_out;
+    na.gamma = (const T*)p.gamma; na.n_eta = n_eta;
+    na.B = (int)B; na.N = N;
+    na.n_tiles = (int)((B + na.epc - 1) / na.epc);
+    na.bc = bc; na.step = step; na.u = uniform_of<T>(e);
+    const long long slots = 2LL * e->sm_count;
+    const int grid = (int)(na.n_tiles < slots ? na.n_tiles : slots);
+    const int rc = U == 2 ? launch_nl_fast<T, 2>(na, grid, fast, e->uniform, e->lamk, stream)
+                          : launch_nl_fast<T, 1>(na, grid, fast, e->uniform, e->lamk, stream);
+    if (rc != MT_OK) return rc;
+    e->launches++;
+  } else {
+    NlScalarArgs<T> sa;
+    sa.in = obs_in; sa.out = obs_out; sa.table = table; sa.flags = flags; sa.action = action;
+    sa.gamma = (const T*)p.gamma; sa.n_eta = n_eta; sa.B = B; sa.N = N; sa.bc = bc; sa.step = step;
+    const long long cells = B * (long long)N;
+    const int block = 256;
+    const long long grid = (cells + block - 1) / block;
+    if (grid > 0x7fffffffLL) return fail(MT_EINVAL, "batch too large for one launch");
+    if (fast) nonlocal_scalar_kernel<T, FastAllowed<T>::value><<<(unsigned)grid, block, 0, stream>>>(sa);
+    else nonlocal_scalar_kernel<T, false><<<(unsigned)grid, block, 0, stream>>>(sa);
+    e->launches++;
+    if (reward_out) {
+      const int wpb = 8;
+      reward_rows_kernel<T><<<(unsigned)((B + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+          (const T*)obs_out, reward_out, B, N);
+      e->launches++;
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  return MT_OK;
+}
+
 // Steps roads [env0, env0 + n_env) of the batch; all pointers address the
 // whole batch (road 0) and are offset here.
 template <typename T>
@@ -312,6 +413,9 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
   const T step = (T)(p.dt / p.dx);
 
   if (g.grid > 0x7fffffffLL) return fail(MT_EINVAL, "batch too large for one launch");
+  if (e->cfg.model == MT_MODEL_NONLOCAL)
+    return step_nonlocal<T>(e, obs_in, action, obs_out, reward_out, table, flags, B, aligned, bc,
+                            step, stream);
   if (g.vector_ok && g.tiles == 1 && !(p.flags & MT_FLAG_NO_PIPELINE)) {
     // persistent TMA-pipelined kernel: tiles of consecutive roads
     int U = pipe_vectors_per_thread();
@@ -419,8 +523,6 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
 
 int step_range(mt_engine* e, const void* obs_in, const void* action, void* obs_out,
                void* reward_out, long long env0, long long n_env, cudaStream_t stream) {
-  if (e->cfg.model == MT_MODEL_NONLOCAL)
-    return fail(MT_EINVAL, "the non-local model has no step kernel yet");
   if (e->cfg.dtype == MT_F64)
     return step_typed<double>(e, obs_in, action, obs_out, reward_out, env0, n_env, stream);
   return step_typed<float>(e, obs_in, action, obs_out, reward_out, env0, n_env, stream);

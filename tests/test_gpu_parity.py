@@ -477,3 +477,110 @@ def test_lwr_interior_mass_telescopes():
     rhs = -0.01 * (f[:, n - 2] - f[:, 0])
     np.testing.assert_allclose(lhs, rhs, rtol=0, atol=1e-11)
     m.close()
+
+
+# --------------------------------------------------------------------------- #
+# non-local look-ahead model (no reference code: parity unpinned; the oracle  #
+# is our own restatement of the cited paper)                                  #
+# --------------------------------------------------------------------------- #
+
+def make_nonlocal(**over):
+    from mbrl_traffic_b200 import NonLocalModel, NONLOCAL_MODEL_PARAMS
+    base = dict(NONLOCAL_MODEL_PARAMS)
+    base.pop("optimizer_cls")
+    extra = {k: over.pop(k) for k in list(over)
+             if k in ("device", "action_is_speed_limit", "fast_math")}
+    base.update(over)
+    return NonLocalModel(None, None, None, None, 0, optimizer_cls=None,
+                         **base, **extra)
+
+
+NL_BCS = ["loop", "extend_both", {"constant_both": (0.3, 0.2)},
+          {"inflow_outflow": 0.3}]
+
+
+@pytest.mark.parametrize("n", [32, 64, 250, 1000, 1024, 33, 1001, 5000])
+@pytest.mark.parametrize("bci", [0, 1, 2, 3])
+@pytest.mark.parametrize("eta,kernel", [(800, "linear"), (200, "constant"),
+                                        (50, "linear")])
+def test_nonlocal_matches_oracle_f64(n, bci, eta, kernel):
+    _need_gpu()
+    bc = NL_BCS[bci]
+    b = 23 if n <= 1024 else 3
+    obs = make_obs(b, n, seed=n + bci)
+    m = make_nonlocal(eta=eta, kernel=kernel, boundary_conditions=bc)
+    out = m.get_next_obs(gpu(obs), None).cpu().numpy()
+    ref = o.nonlocal_step(obs, o.nonlocal_weights(eta, 50, kernel),
+                          boundary_conditions=bc)
+    assert np.array_equal(out, ref)
+    m.close()
+
+
+def test_nonlocal_chained_config3_shape():
+    """Highway with fixed inflow / free outflow, look-ahead 16 cells."""
+    _need_gpu()
+    obs = make_obs(256, 1000, seed=21)
+    bc = {"inflow_outflow": 0.3}
+    m = make_nonlocal(boundary_conditions=bc)
+    out = m.run(gpu(obs), None, n_steps=50).cpu().numpy()
+    g = o.nonlocal_weights(800, 50, "linear")
+    ref = obs
+    for _ in range(50):
+        ref = o.nonlocal_step(ref, g, boundary_conditions=bc)
+    assert np.array_equal(out, ref)
+    host = m.run(obs, None, n_steps=50)
+    assert np.array_equal(host, ref)
+    m.close()
+
+
+def test_nonlocal_ring_conserves_mass_and_respects_bounds_full_size():
+    _need_gpu()
+    b, n = 16384, 1000
+    rng = np.random.default_rng(5)
+    rho = rng.uniform(0.05, 0.9, (b, n))
+    obs = np.concatenate((rho, np.zeros_like(rho)), axis=1)
+    m = make_nonlocal()
+    assert m.cfl_number() <= 1.0
+    out = m.run(gpu(obs), None, n_steps=20).cpu().numpy()
+    r = out[:, :n]
+    assert r.min() >= 0.0 and r.max() <= 1.0
+    np.testing.assert_allclose(r.sum(axis=1), rho.sum(axis=1), rtol=1e-12)
+    m.close()
+
+
+def test_nonlocal_per_env_parameters_and_rewards():
+    _need_gpu()
+    from mbrl_traffic_b200.engine import Engine
+    b, n = 48, 500
+    rng = np.random.default_rng(6)
+    rho_max = rng.choice([1.0, 0.5, 0.2], b)
+    v_max = rng.uniform(10, 30, b)
+    lam = rng.choice([1.0, 2.0], b)
+    rho = rho_max[:, None] * rng.uniform(0.05, 0.9, (b, n))
+    obs = np.concatenate((rho, np.zeros_like(rho)), axis=1)
+    g = o.nonlocal_weights(400, 50, "linear")
+    eng = Engine("nonlocal", "float64", b, n, max_n_eta=64)
+    eng.set_params(dx=50, dt=0.5, rho_max=gpu(rho_max), v_max=gpu(v_max),
+                   lam=gpu(lam), boundary_conditions="loop", gamma=gpu(g))
+    x = gpu(obs)
+    out = torch.empty_like(x)
+    rew = torch.empty(b, dtype=torch.float64, device="cuda:0")
+    eng.step(x, out, reward=rew)
+    ref = o.nonlocal_step(obs, g, rho_max=rho_max, v_max=v_max, lam=lam)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    np.testing.assert_allclose(rew.cpu().numpy(), o.mean_speed_reward(ref),
+                               rtol=1e-12)
+    eng.close()
+
+
+def test_nonlocal_f32_tolerance():
+    _need_gpu()
+    obs32 = make_obs(128, 1000, seed=22, dtype=np.float32)
+    g = o.nonlocal_weights(800, 50, "linear")
+    ref = o.nonlocal_step(obs32.astype(np.float64), g)
+    for fast in (False, True):
+        m = make_nonlocal(fast_math=fast)
+        out = m.get_next_obs(gpu(obs32), None).cpu().numpy()
+        err = np.abs(out - ref) / np.maximum(np.abs(ref), 1.0)
+        assert err.max() <= 2e-6, err.max()
+        m.close()

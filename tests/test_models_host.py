@@ -159,3 +159,25 @@ def test_product_package_never_imports_the_oracle():
                     text = f.read()
                 assert "import oracle" not in text and \
                     "from oracle" not in text, name
+
+
+def test_nonlocal_model_host_contract(tmp_path):
+    from mbrl_traffic_b200 import NonLocalModel, NONLOCAL_MODEL_PARAMS
+    from mbrl_traffic_b200.nonlocal_ import lookahead_weights
+    from oracle import np_oracle
+    m = NonLocalModel(**_params(NONLOCAL_MODEL_PARAMS))
+    assert m.eta == 800 and m.kernel == "linear"
+    g = m.weights()
+    assert g.shape == (16,) and abs(g.sum() - 1) < 1e-14
+    # the product's weights and the oracle's are computed independently
+    assert np.array_equal(g, np_oracle.nonlocal_weights(800, 50, "linear"))
+    assert np.array_equal(lookahead_weights(200, 50, "constant"),
+                          np_oracle.nonlocal_weights(200, 50, "constant"))
+    with pytest.raises(ValueError):
+        lookahead_weights(120, 50)
+    assert m.cfl_number() <= 1.0
+    m.save(str(tmp_path))
+    m2 = NonLocalModel(**_params(NONLOCAL_MODEL_PARAMS))
+    m2.eta, m2.kernel = 100, "constant"
+    m2.load(str(tmp_path / "model.json"))
+    assert m2.eta == 800 and m2.kernel == "linear"

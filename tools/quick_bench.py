@@ -33,15 +33,21 @@ def main():
     ap.add_argument("--fast", action="store_true")
     ap.add_argument("--reward", action="store_true")
     ap.add_argument("--direct", action="store_true")
+    ap.add_argument("--n-eta", type=int, default=16)
     ap.add_argument("--rho-max", type=float, default=1.0)
     args = ap.parse_args()
 
     tdt = torch.float64 if args.dtype == "float64" else torch.float32
     b, n = args.envs, args.cells
-    eng = Engine(args.model, args.dtype, b, n)
+    eng = Engine(args.model, args.dtype, b, n, max_n_eta=256)
+    gamma = None
+    if args.model == "nonlocal":
+        from mbrl_traffic_b200.nonlocal_ import lookahead_weights
+        gamma = torch.as_tensor(lookahead_weights(50.0 * args.n_eta, 50.0),
+                                device="cuda").to(tdt)
     eng.set_params(dx=50, dt=0.5, rho_max=args.rho_max, v_max=30, lam=1,
                    boundary_conditions="loop", tau=9, fast_math=args.fast,
-                   no_pipeline=args.direct)
+                   no_pipeline=args.direct, gamma=gamma)
     rng = np.random.default_rng(0)
     rho = args.rho_max * rng.uniform(0.05, 0.9, (b, n))
     v = 30 * (1 - rho / args.rho_max) + rng.normal(0, 1, (b, n))
