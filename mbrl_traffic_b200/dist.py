@@ -1,0 +1,224 @@
+"""Multi-GPU plumbing: one process per GPU over ``torch.distributed``.
+
+Two ways the path shards:
+
+* **Road batch** -- roads are independent (arz.py:508-513,
+  evaluate_model.py:388-403): ``shard_range`` gives each rank a contiguous
+  range; there is no data-path collective.
+* **One long road** -- ``DomainDecomposedRoad`` splits the cell axis into
+  contiguous blocks with ``halo`` ghost cells per internal edge.  The step
+  kernel leaves ghost edges alone (``MT_BC_HALO``); after every ``halo`` steps
+  neighbouring ranks swap their edge cells (point-to-point send/recv: NCCL on
+  GPUs, gloo in the CPU tests).  Stencil radius is one cell per step for LWR
+  and ARZ, so ``halo`` steps can run between exchanges (temporal blocking:
+  the exchange is latency-bound, 2*halo values per side).
+"""
+import numpy as np
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous ``[lo, hi)`` of ``n_items`` owned by ``rank`` (remainder
+    spread over the first ranks)."""
+    base, rem = divmod(int(n_items), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class DomainDecomposedRoad(object):
+    """One road of ``n_cells`` cells split over the ranks of a process group.
+
+    Parameters
+    ----------
+    n_cells : int
+        global number of cells
+    rank, world : int
+        this rank and the number of ranks
+    halo : int
+        ghost cells per internal edge = steps between exchanges
+    stepper : callable
+        ``stepper(local_obs, bc_left, bc_right) -> new_local_obs`` advancing
+        the local block ``[rho | v]`` (shape ``(2 * n_local,)`` or
+        ``(1, 2 * n_local)``) by one step; ``bc_*`` is ``"physical"`` on a
+        true road end and ``"halo"`` on an internal edge.
+    exchange : callable or None
+        ``exchange(send_left, send_right) -> (recv_left, recv_right)`` with
+        None on missing sides; defaults to ``torch.distributed`` send/recv.
+    """
+
+    def __init__(self, n_cells, rank, world, halo, stepper, exchange=None):
+        if halo < 1:
+            raise ValueError("halo must be >= 1")
+        self.n_cells, self.rank, self.world, self.halo = n_cells, rank, world, halo
+        self.lo, self.hi = shard_range(n_cells, rank, world)
+        if self.hi - self.lo < halo + 1:
+            raise ValueError("blocks must be wider than the halo")
+        self.has_left = rank > 0
+        self.has_right = rank < world - 1
+        self.n_local = (self.hi - self.lo) + halo * (self.has_left + self.has_right)
+        self.stepper = stepper
+        self.exchange = exchange or self._torch_exchange
+        self._since_exchange = 0
+
+    # ------------------------------------------------------------------ #
+    def scatter(self, global_obs):
+        """Cut this rank's block (with ghosts) out of a global ``[rho | v]``."""
+        n, h = self.n_cells, self.halo
+        a = self.lo - (h if self.has_left else 0)
+        b = self.hi + (h if self.has_right else 0)
+        g = np.asarray(global_obs).reshape(-1) if not _is_torch(global_obs) \
+            else global_obs.reshape(-1)
+        rho, v = g[a:b], g[n + a:n + b]
+        if _is_torch(g):
+            import torch
+            return torch.cat((rho, v)).contiguous()
+        return np.concatenate((rho, v))
+
+    def own(self, local_obs):
+        """The cells this rank owns (ghosts stripped) as ``(rho, v)``."""
+        x = local_obs.reshape(-1)
+        h, nl = self.halo, self.n_local
+        a = h if self.has_left else 0
+        b = nl - (h if self.has_right else 0)
+        return x[a:b], x[nl + a:nl + b]
+
+    # ------------------------------------------------------------------ #
+    def needs_refresh(self):
+        """True when the ghost cells have been consumed (``halo`` steps ran)."""
+        return self._since_exchange >= self.halo
+
+    def step(self, local_obs):
+        """One global time step; exchanges halos when the ghosts are used up."""
+        if self.needs_refresh():
+            local_obs = self.refresh(local_obs)
+        out = self.stepper(local_obs,
+                           "halo" if self.has_left else "physical",
+                           "halo" if self.has_right else "physical")
+        self._since_exchange += 1
+        return out
+
+    def edge_cells(self, local_obs):
+        """``(send_left, send_right)``: my first / last ``halo`` own cells as
+        ``[rho(h) | v(h)]`` (None on a true road end)."""
+        x = local_obs.reshape(-1)
+        h, nl = self.halo, self.n_local
+        a = h if self.has_left else 0            # first own cell
+        b = nl - (h if self.has_right else 0)    # one past the last own cell
+        cat = _cat(x)
+        send_l = cat((x[a:a + h], x[nl + a:nl + a + h])) if self.has_left else None
+        send_r = cat((x[b - h:b], x[nl + b - h:nl + b])) if self.has_right else None
+        return send_l, send_r
+
+    def set_ghosts(self, local_obs, recv_l, recv_r):
+        """Write the neighbours' edge cells into my ghost cells (in place)."""
+        x = local_obs.reshape(-1)
+        h, nl = self.halo, self.n_local
+        b = nl - (h if self.has_right else 0)
+        if self.has_left:
+            x[0:h] = recv_l[:h]
+            x[nl:nl + h] = recv_l[h:]
+        if self.has_right:
+            x[b:b + h] = recv_r[:h]
+            x[nl + b:nl + b + h] = recv_r[h:]
+        self._since_exchange = 0
+        return local_obs
+
+    def refresh(self, local_obs):
+        """Swap edge cells with the neighbours."""
+        send_l, send_r = self.edge_cells(local_obs)
+        recv_l, recv_r = self.exchange(send_l, send_r)
+        return self.set_ghosts(local_obs, recv_l, recv_r)
+
+    def _torch_exchange(self, send_l, send_r):
+        import torch
+        import torch.distributed as dist
+        probe = send_l if send_l is not None else send_r
+        was_numpy = probe is not None and not _is_torch(probe)
+        ops, recv_l, recv_r = [], None, None
+        if send_l is not None:
+            send_l = _as_tensor(send_l)
+            recv_l = torch.empty_like(send_l)
+            ops += [dist.P2POp(dist.isend, send_l, self.rank - 1),
+                    dist.P2POp(dist.irecv, recv_l, self.rank - 1)]
+        if send_r is not None:
+            send_r = _as_tensor(send_r)
+            recv_r = torch.empty_like(send_r)
+            ops += [dist.P2POp(dist.isend, send_r, self.rank + 1),
+                    dist.P2POp(dist.irecv, recv_r, self.rank + 1)]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        if was_numpy:
+            recv_l = None if recv_l is None else recv_l.numpy()
+            recv_r = None if recv_r is None else recv_r.numpy()
+        return recv_l, recv_r
+
+    def gather(self, local_obs):
+        """All ranks' own cells assembled into the global ``[rho | v]`` on
+        every rank (for checks and output, not on the hot path)."""
+        import torch
+        import torch.distributed as dist
+        rho, v = self.own(local_obs)
+        mine = _as_tensor(_cat(rho)((rho, v))).contiguous()
+        sizes = [2 * (shard_range(self.n_cells, r, self.world)[1]
+                      - shard_range(self.n_cells, r, self.world)[0])
+                 for r in range(self.world)]
+        parts = [torch.empty(s, dtype=mine.dtype, device=mine.device) for s in sizes]
+        dist.all_gather(parts, mine) if len(set(sizes)) == 1 else \
+            _all_gather_ragged(parts, mine, self.rank, self.world)
+        rhos = [p[:p.numel() // 2] for p in parts]
+        vs = [p[p.numel() // 2:] for p in parts]
+        return torch.cat(rhos + vs)
+
+
+def _all_gather_ragged(parts, mine, rank, world):
+    import torch.distributed as dist
+    for r in range(world):
+        if r == rank:
+            parts[r].copy_(mine)
+        dist.broadcast(parts[r], src=r)
+
+
+def _is_torch(x):
+    return hasattr(x, "data_ptr")   # (NumPy 2 arrays also have `.device`)
+
+
+def _cat(x):
+    if _is_torch(x):
+        import torch
+        return torch.cat
+    return np.concatenate
+
+
+def _as_tensor(x):
+    import torch
+    if _is_torch(x):
+        return x.contiguous()
+    return torch.from_numpy(np.ascontiguousarray(x))
+
+
+def engine_stepper(engine, physical_left, physical_right, left_val=(0.0, 0.0),
+                   right_val=(0.0, 0.0), **params):
+    """A ``stepper`` for ``DomainDecomposedRoad`` backed by one ``Engine``
+    sized for the local block; ``physical_*`` are ``mt_bc`` codes of the true
+    road ends (``_lib.MT_BC_EXTEND`` / ``MT_BC_CONSTANT``)."""
+    import torch
+    from mbrl_traffic_b200 import _lib
+    state = {"bc": None, "buf": None}
+
+    def step(local_obs, bc_left, bc_right):
+        cl = _lib.MT_BC_HALO if bc_left == "halo" else physical_left
+        cr = _lib.MT_BC_HALO if bc_right == "halo" else physical_right
+        if state["bc"] != (cl, cr):
+            engine.set_params(
+                boundary_conditions={"codes": (cl, cr, left_val, right_val)},
+                **params)
+            state["bc"] = (cl, cr)
+        x = local_obs.reshape(1, -1)
+        if state["buf"] is None or state["buf"].data_ptr() == x.data_ptr():
+            state["buf"] = torch.empty_like(x)
+        out = state["buf"]
+        engine.step(x, out)
+        state["buf"] = x          # ping-pong
+        return out.reshape(local_obs.shape)
+
+    return step

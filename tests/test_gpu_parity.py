@@ -584,3 +584,58 @@ def test_nonlocal_f32_tolerance():
         err = np.abs(out - ref) / np.maximum(np.abs(ref), 1.0)
         assert err.max() <= 2e-6, err.max()
         m.close()
+
+
+# --------------------------------------------------------------------------- #
+# one long road, domain-decomposed (ranks emulated on one GPU; the real       #
+# multi-rank run is tools/multi_gpu_check.py under torchrun)                   #
+# --------------------------------------------------------------------------- #
+
+@pytest.mark.parametrize("kind", ["lwr", "arz"])
+@pytest.mark.parametrize("world,halo,n", [(2, 1, 4096), (4, 8, 40000), (8, 16, 100000)])
+def test_domain_decomposition_emulated(kind, world, halo, n):
+    _need_gpu()
+    from mbrl_traffic_b200 import _lib
+    from mbrl_traffic_b200.dist import DomainDecomposedRoad, engine_stepper
+    from mbrl_traffic_b200.engine import Engine
+    steps = 40
+    params = dict(dx=50, dt=0.5, rho_max=1, v_max=30, lam=1, tau=9)
+    road = make_obs(1, n, seed=31)[0]
+    # reference: the whole road on one engine
+    full = Engine(kind, "float64", 1, n)
+    full.set_params(boundary_conditions="extend_both", **params)
+    a = gpu(road).reshape(1, -1).clone()
+    b = torch.empty_like(a)
+    ref = full.rollout(a, b, steps).cpu().numpy()[0]
+    # oracle agrees with the single-engine run
+    cur = road
+    for _ in range(steps):
+        cur = oracle_step(kind, cur, boundary_conditions="extend_both")
+    assert np.array_equal(ref, cur)
+
+    ranks, local = [], []
+    for r in range(world):
+        probe = DomainDecomposedRoad(n, r, world, halo, None,
+                                     exchange=lambda *_: (None, None))
+        eng = Engine(kind, "float64", 1, probe.n_local)
+        probe.stepper = engine_stepper(eng, _lib.MT_BC_EXTEND, _lib.MT_BC_EXTEND,
+                                       **params)
+        ranks.append(probe)
+        local.append(probe.scatter(gpu(road)).clone())
+    for _ in range(steps):
+        if ranks[0].needs_refresh():
+            edges = [d.edge_cells(x) for d, x in zip(ranks, local)]
+            for r, d in enumerate(ranks):
+                d.set_ghosts(local[r],
+                             edges[r - 1][1] if d.has_left else None,
+                             edges[r + 1][0] if d.has_right else None)
+        new = []
+        for d, x in zip(ranks, local):
+            new.append(d.stepper(x, "halo" if d.has_left else "physical",
+                                 "halo" if d.has_right else "physical"))
+            d._since_exchange += 1
+        local = new
+    torch.cuda.synchronize()
+    rho = torch.cat([d.own(x)[0] for d, x in zip(ranks, local)]).cpu().numpy()
+    v = torch.cat([d.own(x)[1] for d, x in zip(ranks, local)]).cpu().numpy()
+    assert np.array_equal(np.concatenate((rho, v)), ref)
