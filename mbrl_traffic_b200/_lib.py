@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmtraffic.so")
+# MT_LIB selects an alternative build of the same library (tuning experiments)
+LIB_PATH = os.environ.get("MT_LIB") or os.path.join(_HERE, "libmtraffic.so")
 
 MT_OK, MT_EINVAL, MT_ECUDA, MT_ENOMEM, MT_ESTATE = 0, -1, -2, -3, -4
 MT_MODEL_LWR, MT_MODEL_ARZ, MT_MODEL_NONLOCAL = 0, 1, 2

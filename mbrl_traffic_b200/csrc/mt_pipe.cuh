@@ -29,15 +29,19 @@
 
 namespace mt {
 
+#ifndef MT_PIPE_CTAS
+#define MT_PIPE_CTAS 2                            // resident CTAs per SM the kernel is sized for
+#endif
+constexpr int PIPE_CTAS = MT_PIPE_CTAS;
 constexpr int PIPE_BLOCK = 512;                   // consumer threads at U = 1
-constexpr int PIPE_OUT = 2;
+constexpr int PIPE_OUT = (PIPE_CTAS >= 3) ? 1 : 2;
 constexpr int PIPE_TILE_BYTES = PIPE_BLOCK * 32;  // 16 KB
 constexpr int PIPE_MAX_EPC = 64;                  // roads per tile (cap)
 // input stages: as many as fit next to the exchange arrays with two CTAs per SM
 template <typename T, int U> struct PipeCfg {
   static constexpr int NC = PIPE_BLOCK / U;                     // consumer threads
   static constexpr int XCH = NC + PIPE_MAX_EPC + 8;             // one pad slot per road
-  static constexpr int STAGES = (sizeof(T) == 8 && U == 1) ? 3 : 4;
+  static constexpr int STAGES = (PIPE_CTAS >= 3) ? 2 : (sizeof(T) == 8 && U == 1) ? 3 : 4;
 };
 
 // ---- PTX wrappers -----------------------------------------------------------
@@ -99,6 +103,15 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t 
 template <int N> __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
+// Programmatic dependent launch: let the next kernel in the stream start its
+// prologue while this one drains, and block until the previous kernel's
+// writes are visible.  Both are no-ops for an ordinary launch.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait_prior_grid() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 // barrier among the consumer threads only (id 1; id 0 is __syncthreads)
 __device__ __forceinline__ void consumer_sync(int nc) {
   asm volatile("bar.sync 1, %0;" ::"r"(nc) : "memory");
@@ -138,10 +151,10 @@ template <typename T, int U> struct PipeSmem {
   uint64_t out_free[PIPE_OUT];              // producer -> consumers: store drained
 };
 // two CTAs per SM: 2 x (smem + 1 KB reserved) <= 228 KB
-static_assert(sizeof(PipeSmem<double, 1>) <= 113 * 1024, "f64 U=1 does not fit twice per SM");
-static_assert(sizeof(PipeSmem<double, 2>) <= 113 * 1024, "f64 U=2 does not fit twice per SM");
-static_assert(sizeof(PipeSmem<float, 1>) <= 113 * 1024, "f32 U=1 does not fit twice per SM");
-static_assert(sizeof(PipeSmem<float, 2>) <= 113 * 1024, "f32 U=2 does not fit twice per SM");
+static_assert(sizeof(PipeSmem<double, 2>) <= (228 / PIPE_CTAS - 1) * 1024, "f64 U=2 smem");
+static_assert(sizeof(PipeSmem<float, 2>) <= (228 / PIPE_CTAS - 1) * 1024, "f32 U=2 smem");
+static_assert(PIPE_CTAS >= 3 || sizeof(PipeSmem<double, 1>) <= 113 * 1024, "f64 U=1 smem");
+static_assert(PIPE_CTAS >= 3 || sizeof(PipeSmem<float, 1>) <= 113 * 1024, "f32 U=1 smem");
 
 template <typename T> struct PipeArgs {
   const T* in;
@@ -167,7 +180,7 @@ template <typename T> struct PipeArgs {
 // LAM_RUNTIME.  UNIFORM: every road shares the scalar parameters in a.u.
 // U: 16-byte vectors (of each field) per thread; a thread owns U*V cells.
 template <typename T, int MODEL, bool FAST, int LAMK, bool UNIFORM, int U>
-__global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) step_pipe_kernel(const PipeArgs<T> a) {
+__global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kernel(const PipeArgs<T> a) {
   constexpr int V = Vec<T>::N;
   constexpr int CPT = U * V;
   constexpr bool ARZ = (MODEL == 1);
@@ -190,6 +203,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) step_pipe_kernel(const
   const uint32_t full0 = smem_u32(&sm.full[0]), empty0 = smem_u32(&sm.empty[0]);
   const uint32_t ofull0 = smem_u32(&sm.out_full[0]), ofree0 = smem_u32(&sm.out_free[0]);
 
+  pdl_launch_dependents();
   // pad slots of the exchange arrays stay zero for the kernel's life: they
   // feed the (discarded) left-face flux of each road's first cell
   for (int i = t; i < 2 * PIPE_XCH; i += blockDim.x) { (&sm.xD[0][0])[i] = T(0); (&sm.xR[0][0])[i] = T(0); }
@@ -205,6 +219,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) step_pipe_kernel(const
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait_prior_grid();  // everything above overlapped the previous kernel's tail
 
   // ======================= producer warp ===================================
   if (t >= NC) {
@@ -217,14 +232,33 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) step_pipe_kernel(const
       auto issue_load = [&](int i) {
         const int tile = (int)blockIdx.x + i * (int)gridDim.x;
         const int s = i % PIPE_STAGES;
-        const uint32_t bytes = bytes_of(tile);
-        mbar_expect_tx(full0 + 8 * s, bytes);
-        bulk_load(in0 + (uint32_t)s * PIPE_TILE_BYTES, gin + (size_t)tile * tile_bytes, bytes,
-                  full0 + 8 * s);
+        if (ARZ) {
+          const uint32_t bytes = bytes_of(tile);
+          mbar_expect_tx(full0 + 8 * s, bytes);
+          bulk_load(in0 + (uint32_t)s * PIPE_TILE_BYTES, gin + (size_t)tile * tile_bytes, bytes,
+                    full0 + 8 * s);
+        } else {
+          // LWR ignores the input velocity (lwr.py:197): fetch the density half
+          // of each road only, at its usual place in the stage
+          const int envs = tile == last_tile ? last_envs : a.epc;
+          const uint32_t half = row_bytes >> 1;
+          mbar_expect_tx(full0 + 8 * s, (uint32_t)envs * half);
+          for (int r = 0; r < envs; ++r)
+            bulk_load(in0 + (uint32_t)s * PIPE_TILE_BYTES + (uint32_t)r * row_bytes,
+                      gin + (size_t)tile * tile_bytes + (size_t)r * row_bytes, half,
+                      full0 + 8 * s);
+        }
       };
       auto prefetch = [&](int i) {
         const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-        bulk_prefetch_l2(gin + (size_t)tile * tile_bytes, bytes_of(tile));
+        if (ARZ) {
+          bulk_prefetch_l2(gin + (size_t)tile * tile_bytes, bytes_of(tile));
+        } else {
+          const int envs = tile == last_tile ? last_envs : a.epc;
+          for (int r = 0; r < envs; ++r)
+            bulk_prefetch_l2(gin + (size_t)tile * tile_bytes + (size_t)r * row_bytes,
+                             row_bytes >> 1);
+        }
       };
       const int pre = n_my < PIPE_STAGES ? n_my : PIPE_STAGES;
       for (int i = 0; i < pre; ++i) issue_load(i);

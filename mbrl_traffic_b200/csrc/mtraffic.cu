@@ -190,6 +190,16 @@ Geometry plan(long long B, int N, int V, bool aligned) {
   return g;
 }
 
+// programmatic dependent launch of back-to-back step kernels (MT_PDL=0 disables)
+bool pipe_use_pdl() {
+  static int v = -1;
+  if (v < 0) {
+    const char* s = getenv("MT_PDL");
+    v = (s && s[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 template <typename T, int MODEL, bool FAST, int LAMK, bool UNIFORM, int U>
 int launch_pipe(const PipeArgs<T>& pa, int grid, cudaStream_t stream) {
   static bool configured = false;  // per instantiation; the attribute is per function
@@ -199,7 +209,17 @@ int launch_pipe(const PipeArgs<T>& pa, int grid, cudaStream_t stream) {
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  step_pipe_kernel<T, MODEL, FAST, LAMK, UNIFORM, U><<<grid, pa.nc + 32, smem, stream>>>(pa);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)(pa.nc + 32));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pipe_use_pdl() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, step_pipe_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>, pa));
   return MT_OK;
 }
 
@@ -443,7 +463,7 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
     pa.bc = bc;
     pa.step = step;
     pa.u = uniform_of<T>(e);
-    const long long slots = 2LL * e->sm_count;
+    const long long slots = (long long)PIPE_CTAS * e->sm_count;
     const int grid = (int)(n_tiles < slots ? n_tiles : slots);
     int rc;
     if (e->cfg.model == MT_MODEL_ARZ)

@@ -66,13 +66,13 @@ def main():
     # ---- 2. one long road ------------------------------------------------
     n_road = int(os.environ.get("MT_ROAD_CELLS", 10_000_000))
     halo = int(os.environ.get("MT_HALO", 32))
-    steps = 2 * halo
+    steps = 8 * halo
     road = torch.as_tensor(make_obs(1, n_road, 2)[0], device=dev)
     d = DomainDecomposedRoad(n_road, rank, world, halo, None)
     eng = Engine("arz", "float64", 1, d.n_local, device=local_rank)
     d.stepper = engine_stepper(eng, _lib.MT_BC_EXTEND, _lib.MT_BC_EXTEND, **PARAMS)
     local = d.scatter(road).clone()
-    for _ in range(halo):                     # warm-up incl. one exchange
+    for _ in range(2 * halo + 1):             # warm-up incl. two exchanges (NCCL set-up)
         local = d.step(local)
     local = d.scatter(road).clone()
     d._since_exchange = 0
