@@ -64,17 +64,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// try_wait parks the warp in hardware for up to this long before it returns
+// false, instead of spinning through issue slots other warps could use
+#ifndef MT_MBAR_HINT_NS
+#define MT_MBAR_HINT_NS 2000
+#endif
+constexpr uint32_t MBAR_SUSPEND_HINT_NS = MT_MBAR_HINT_NS;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
       "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
       "@P1 bra DONE;\n"
       "bra LAB_WAIT;\n"
       "DONE:\n"
       "}" ::"r"(bar),
-      "r"(parity)
+      "r"(parity), "r"(MBAR_SUSPEND_HINT_NS)
       : "memory");
 }
 // global -> shared, completion counted in bytes on an mbarrier
