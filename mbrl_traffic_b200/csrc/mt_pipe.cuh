@@ -70,6 +70,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 #define MT_MBAR_HINT_NS 2000
 #endif
 constexpr uint32_t MBAR_SUSPEND_HINT_NS = MT_MBAR_HINT_NS;
+#ifndef MT_PRODUCER_NAP_NS
+#define MT_PRODUCER_NAP_NS 100
+#endif
+constexpr unsigned PRODUCER_NAP_NS = MT_PRODUCER_NAP_NS;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -82,6 +86,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar),
       "r"(parity), "r"(MBAR_SUSPEND_HINT_NS)
       : "memory");
+}
+// The producer thread sits alone in its warp: between polls it sleeps, so that
+// its spinning does not take issue slots from the consumer warps that share
+// its scheduler.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, unsigned ns) {
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(ns);
+  }
 }
 // global -> shared, completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src_gmem, uint32_t bytes,
@@ -275,10 +298,10 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
         const int s = i % PIPE_STAGES, o = i % PIPE_OUT;
         if (ahead > 0 && i + PIPE_STAGES + ahead < n_my) prefetch(i + PIPE_STAGES + ahead);
         if (i + PIPE_STAGES < n_my) {  // refill stage s once the consumers have read tile i
-          mbar_wait(empty0 + 8 * s, (uint32_t)((i / PIPE_STAGES) & 1));
+          mbar_wait_relaxed(empty0 + 8 * s, (uint32_t)((i / PIPE_STAGES) & 1), PRODUCER_NAP_NS);
           issue_load(i + PIPE_STAGES);
         }
-        mbar_wait(ofull0 + 8 * o, (uint32_t)((i / PIPE_OUT) & 1));
+        mbar_wait_relaxed(ofull0 + 8 * o, (uint32_t)((i / PIPE_OUT) & 1), PRODUCER_NAP_NS);
         bulk_store(gout + (size_t)tile * tile_bytes, out0 + (uint32_t)o * PIPE_TILE_BYTES,
                    bytes_of(tile));
         bulk_commit();

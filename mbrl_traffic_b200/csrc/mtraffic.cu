@@ -13,6 +13,7 @@
 #include "mtraffic.h"
 #include "mt_math.cuh"
 #include "mt_pipe.cuh"
+#include "mt_ring.cuh"
 #include "mt_direct.cuh"
 #include "mt_nonlocal.cuh"
 
@@ -200,18 +201,25 @@ bool pipe_use_pdl() {
   return v != 0;
 }
 
-template <typename T, int MODEL, bool FAST, int LAMK, bool UNIFORM, int U>
-int launch_pipe(const PipeArgs<T>& pa, int grid, cudaStream_t stream) {
-  static bool configured = false;  // per instantiation; the attribute is per function
-  const size_t smem = sizeof(PipeSmem<T, U>);
-  if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(step_pipe_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+// Which persistent kernel: the producer-warp one (mt_pipe.cuh) measured faster
+// in f64 and f32 FAST, the producer-less ring (mt_ring.cuh) in f32 EXACT
+// (B200, 16384x1000: 87/88 % vs 80/82 % and 71 % vs 81 % of HBM peak).
+// MT_KERNEL=pipe|ring overrides for A/B runs.
+bool pipe_use_ring(bool is_f32, bool fast) {
+  static int v = -1;
+  if (v < 0) {
+    const char* s = getenv("MT_KERNEL");
+    v = !s ? 2 : (s[0] == 'r') ? 1 : 0;
   }
+  if (v == 2) return is_f32 && !fast;
+  return v != 0;
+}
+
+template <typename K, typename Args>
+int launch_pdl(K kernel, const Args& args, int grid, int block, size_t smem, cudaStream_t stream) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3((unsigned)(pa.nc + 32));
+  cfg.blockDim = dim3((unsigned)block);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -219,8 +227,27 @@ int launch_pipe(const PipeArgs<T>& pa, int grid, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = pipe_use_pdl() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, step_pipe_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>, pa));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, args));
   return MT_OK;
+}
+
+template <typename T, int MODEL, bool FAST, int LAMK, bool UNIFORM, int U>
+int launch_pipe(const PipeArgs<T>& pa, int grid, cudaStream_t stream) {
+  static bool configured = false;  // per instantiation; the attribute is per function
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(step_pipe_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(PipeSmem<T, U>)));
+    CUDA_TRY(cudaFuncSetAttribute(step_ring_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(RingSmem<T, U>)));
+    configured = true;
+  }
+  if (pipe_use_ring(sizeof(T) == 4, FAST))
+    return launch_pdl(step_ring_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>, pa, grid, pa.nc,
+                      sizeof(RingSmem<T, U>), stream);
+  return launch_pdl(step_pipe_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>, pa, grid, pa.nc + 32,
+                    sizeof(PipeSmem<T, U>), stream);
 }
 
 template <typename T, int MODEL, bool FAST, int U>
