@@ -1,0 +1,180 @@
+"""Model-based rollouts on the batched engine.
+
+The reference's intended MBRL loop -- a policy proposing speed limits, the
+macroscopic model predicting the outcome, rewards summed over a horizon -- is
+a stub there (``policies/kshoot.py:65-85`` raises ``NotImplementedError``).
+This module is the thin PyTorch side of that loop; every model step is one
+``mt_step`` / ``mt_rollout`` call and no tensor leaves the GPU inside a
+rollout.
+
+Conventions follow the reference's VSL environments
+(``mbrl_traffic/envs/vsl.py``): the action is a speed limit in
+``[0, v_max_max]`` (``vsl.py:92-100``), one per road; the reward is the mean
+speed of the vehicles (``vsl.py:115-118``), whose macroscopic analogue is the
+density-weighted mean speed ``sum(rho v) / sum(rho)`` that the step kernel
+reduces per road.
+"""
+import torch
+from torch import nn
+
+from mbrl_traffic_b200.engine import dtype_name
+
+
+class BatchedMacroEnv(object):
+    """Gym-style facade over a batch of macroscopic roads on one GPU.
+
+    ``model`` is an ``LWRModel`` / ``ARZModel`` / ``NonLocalModel``; its
+    parameters define the dynamics.  Observations are ``(B, 2N)`` device
+    tensors ``[rho | v]``.
+    """
+
+    def __init__(self, model, n_envs, n_cells, horizon=500, dtype=torch.float64,
+                 device=None):
+        self.model = model
+        self.n_envs, self.n_cells, self.horizon = n_envs, n_cells, horizon
+        self.dtype = dtype
+        self.device = torch.device(device if device is not None
+                                   else "cuda:%d" % model.device)
+        self.engine = model._get_engine(n_envs, n_cells, dtype_name(dtype), host=False)
+        self._bufs = [torch.empty(n_envs, 2 * n_cells, dtype=dtype, device=self.device)
+                      for _ in range(2)]
+        self._cur = 0
+        self.reward = torch.empty(n_envs, dtype=dtype, device=self.device)
+        self.t = 0
+
+    @property
+    def obs(self):
+        return self._bufs[self._cur]
+
+    def reset(self, obs0):
+        """Start an episode from ``obs0`` (copied)."""
+        self._cur = 0
+        self._bufs[0].copy_(obs0)
+        self.t = 0
+        return self.obs
+
+    def step(self, action=None):
+        """Advance every road by one step under speed limits ``action``
+        (``(B,)`` device tensor in the env dtype, or None to keep ``v_max``).
+        Returns ``(obs, reward, done, info)``; ``reward`` is a device tensor
+        that the next call overwrites."""
+        self.model._sync_params(
+            (self.n_envs, self.n_cells, dtype_name(self.dtype), self.model.device, False),
+            self.engine)
+        src, dst = self._bufs[self._cur], self._bufs[1 - self._cur]
+        self.engine.step(src, dst, action=action, reward=self.reward)
+        self._cur = 1 - self._cur
+        self.t += 1
+        return self.obs, self.reward, self.t >= self.horizon, {}
+
+
+class FeedForwardActor(nn.Module):
+    """``[2N -> 256 -> 256 -> 1]`` actor, the shape of the reference's SAC
+    policy network (``policies/sac.py:303-322``, ``utils/train.py:152``); the
+    output is squashed to a speed limit in ``[0, v_max_max]``."""
+
+    def __init__(self, obs_dim, v_max_max=30.0, hidden=(256, 256)):
+        super(FeedForwardActor, self).__init__()
+        layers, last = [], obs_dim
+        for h in hidden:
+            layers += [nn.Linear(last, h), nn.ReLU()]
+            last = h
+        layers.append(nn.Linear(last, 1))
+        self.net = nn.Sequential(*layers)
+        self.v_max_max = float(v_max_max)
+
+    def forward(self, obs):
+        x = self.net(obs.to(self.net[0].weight.dtype))
+        return (0.5 * self.v_max_max) * (torch.tanh(x.squeeze(-1)) + 1.0)
+
+
+def policy_rollout(env, actor, obs0, horizon=None, use_graph=True):
+    """Roll ``actor`` through ``env`` for ``horizon`` steps; returns the sum
+    of rewards per road (device tensor).  With ``use_graph`` two consecutive
+    (policy, step) iterations -- one per ping-pong direction -- are captured
+    in a CUDA graph and replayed, so the loop has no per-step launch cost."""
+    horizon = env.horizon if horizon is None else horizon
+    env.reset(obs0)
+    total = torch.zeros(env.n_envs, dtype=env.dtype, device=env.device)
+
+    def one():
+        with torch.no_grad():
+            act = actor(env.obs).to(env.dtype).contiguous()
+        _, r, _, _ = env.step(act)
+        total.add_(r)
+
+    if not use_graph or horizon < 4:
+        for _ in range(horizon):
+            one()
+        return total
+
+    stream = torch.cuda.Stream(device=env.device)
+    stream.wait_stream(torch.cuda.current_stream(env.device))
+    with torch.cuda.stream(stream):
+        one()
+        one()                                   # warm-up both directions
+        torch.cuda.synchronize(env.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            one()
+            one()
+        done = 2
+        while done + 2 <= horizon:
+            graph.replay()
+            done += 2
+        for _ in range(horizon - done):
+            one()
+    torch.cuda.current_stream(env.device).wait_stream(stream)
+    return total
+
+
+class KShootPolicy(object):
+    """Random-shooting MPC over the model (the reference's ``KShootPolicy``,
+    ``policies/kshoot.py:7-85``, whose ``get_action`` is unimplemented;
+    parameters ``num_particles`` / ``traj_length`` from
+    ``utils/train.py:130-135``).
+
+    For every road, ``num_particles`` speed-limit sequences of length
+    ``traj_length`` are sampled uniformly in ``[0, v_max_max]``, all
+    ``B x num_particles`` copies are rolled through the model in one
+    ``mt_rollout`` call, and the first action of the best-return sequence is
+    returned.
+    """
+
+    def __init__(self, model, n_envs, n_cells, num_particles=16, traj_length=10,
+                 v_max_max=30.0, dtype=torch.float64, seed=0):
+        if not model.action_is_speed_limit:
+            raise ValueError("the model must be built with action_is_speed_limit=True")
+        self.model = model
+        self.n_envs, self.n_cells = n_envs, n_cells
+        self.num_particles, self.traj_length = num_particles, traj_length
+        self.v_max_max, self.dtype = float(v_max_max), dtype
+        self.device = torch.device("cuda:%d" % model.device)
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(seed)
+        total = n_envs * num_particles
+        self.engine = model._get_engine(total, n_cells, dtype_name(dtype), host=False)
+        self._a = torch.empty(total, 2 * n_cells, dtype=dtype, device=self.device)
+        self._b = torch.empty_like(self._a)
+        self._rew = torch.empty(traj_length, total, dtype=dtype, device=self.device)
+
+    def sample_actions(self):
+        """``(traj_length, B * num_particles)`` speed limits; particle p of
+        road b sits at column ``b * num_particles + p``."""
+        u = torch.rand(self.traj_length, self.n_envs * self.num_particles,
+                       generator=self.gen, device=self.device, dtype=self.dtype)
+        return u * self.v_max_max
+
+    def get_action(self, obs, actions=None):
+        """Best first action per road, ``(B,)``; also returns the returns of
+        all particles ``(B, num_particles)``."""
+        if actions is None:
+            actions = self.sample_actions()
+        k = self.num_particles
+        self._a.copy_(obs.repeat_interleave(k, dim=0))
+        self.engine.rollout(self._a, self._b, self.traj_length,
+                            actions=actions.contiguous(), rewards=self._rew)
+        returns = self._rew.sum(dim=0).view(self.n_envs, k)
+        best = returns.argmax(dim=1)
+        first = actions[0].view(self.n_envs, k)
+        return first.gather(1, best[:, None]).squeeze(1), returns

@@ -639,3 +639,170 @@ def test_domain_decomposition_emulated(kind, world, halo, n):
     rho = torch.cat([d.own(x)[0] for d, x in zip(ranks, local)]).cpu().numpy()
     v = torch.cat([d.own(x)[1] for d, x in zip(ranks, local)]).cpu().numpy()
     assert np.array_equal(np.concatenate((rho, v)), ref)
+
+
+# --------------------------------------------------------------------------- #
+# edge cases: zeros, NaNs, equilibrium, tiny and ragged shapes                #
+# --------------------------------------------------------------------------- #
+
+@pytest.mark.parametrize("n", [3, 4, 8, 1000])
+def test_exact_zero_density_follows_the_closed_form(n):
+    """rho == 0 makes P = Q * (0/0) NaN in the reference formula
+    (arz.py:411); the kernel's division fallback must produce the same NaNs
+    and the same 1e-10 density patch (arz.py:274-275) as the oracle."""
+    _need_gpu()
+    obs = make_obs(9, n, seed=41)
+    obs[:, n // 2] = 0.0                      # an empty cell in every road
+    obs[0, :n] = 0.0                          # and one completely empty road
+    for bc in ("loop", "extend_both"):
+        m = make_model("arz", boundary_conditions=bc)
+        out = m.get_next_obs(gpu(obs), None).cpu().numpy()
+        with np.errstate(all="ignore"):
+            ref = o.arz_step(obs, boundary_conditions=bc)
+        assert np.array_equal(out, ref, equal_nan=True)
+        assert np.isnan(ref).any()
+        m.close()
+    m = make_model("lwr")
+    out = m.get_next_obs(gpu(obs), None).cpu().numpy()
+    assert np.array_equal(out, o.lwr_step(obs))
+    m.close()
+
+
+def test_exact_equilibrium_takes_the_zero_numerator_path():
+    """v == V(rho) gives y == 0 exactly: the inline division's range test
+    fails on purpose and the zero-admitting re-test must keep the result
+    exact."""
+    _need_gpu()
+    rng = np.random.default_rng(42)
+    rho = rng.uniform(0.05, 0.9, (64, 1000))
+    obs = np.concatenate((rho, 30 * (1 - rho)), axis=1)
+    m = make_model("arz")
+    out = m.run(gpu(obs), None, n_steps=5).cpu().numpy()
+    ref = obs
+    for _ in range(5):
+        ref = o.arz_step(ref)
+    assert np.array_equal(out, ref)
+    m.close()
+
+
+def test_nan_and_inf_inputs_stay_local_and_visible():
+    """Non-finite inputs are outside the parity domain (the kernel selects
+    where NumPy multiplies by a 0/1 mask, so inf*0 differs), but they must
+    neither leak beyond the stencil radius nor be silently replaced by finite
+    numbers."""
+    _need_gpu()
+    n = 64
+    obs = make_obs(6, n, seed=43)
+    poison = {1: (10, 10), 2: (20, n + 20), 3: (5, 5), 4: (7, n + 7)}
+    obs[1, 10] = np.nan          # density
+    obs[2, n + 20] = np.nan      # velocity
+    obs[3, 5] = np.inf
+    obs[4, n + 7] = -np.inf
+    for kind in ("lwr", "arz"):
+        m = make_model(kind)
+        out = m.get_next_obs(gpu(obs), None).cpu().numpy()
+        with np.errstate(all="ignore"):
+            ref = oracle_step(kind, obs)
+        assert np.array_equal(out[[0, 5]], ref[[0, 5]])
+        for row, (cell, idx) in poison.items():
+            if kind == "lwr" and idx >= n:
+                assert np.array_equal(out[row], ref[row])   # v is ignored
+                continue
+            far = np.abs(np.arange(n) - cell) >= 3
+            far[[0, n - 1]] = True
+            keep = np.concatenate((far, far))
+            assert np.array_equal(out[row][keep], ref[row][keep])
+            assert not (np.isfinite(out[row, cell])
+                        and np.isfinite(out[row, n + cell]))
+        m.close()
+
+
+@pytest.mark.parametrize("kind", ["lwr", "arz"])
+@pytest.mark.parametrize("b,n", [(1, 3), (1, 4), (2, 8), (1, 1000), (100003, 8),
+                                 (4097, 30), (515, 1000), (3, 2048), (1, 65536)])
+def test_ragged_and_extreme_shapes(kind, b, n):
+    _need_gpu()
+    obs = make_obs(b, n, seed=b + n)
+    m = make_model(kind)
+    out = m.get_next_obs(gpu(obs), None).cpu().numpy()
+    assert np.array_equal(out, oracle_step(kind, obs))
+    m.close()
+
+
+def test_engine_rejects_bad_arguments():
+    _need_gpu()
+    from mbrl_traffic_b200.engine import Engine
+    with pytest.raises(ValueError):
+        Engine("arz", "float64", 0, 100)
+    with pytest.raises(ValueError):
+        Engine("arz", "float64", 4, 2)
+    eng = Engine("arz", "float64", 4, 16)
+    x = gpu(make_obs(4, 16))
+    with pytest.raises(Exception):        # step before set_params
+        eng.step(x, torch.empty_like(x))
+    eng.set_params(dx=50, dt=0.5, rho_max=1, v_max=30, lam=1,
+                   boundary_conditions="loop", tau=9)
+    with pytest.raises(ValueError):       # in == out
+        eng.step(x, x)
+    with pytest.raises(ValueError):
+        eng.set_params(dx=0, dt=0.5, rho_max=1, v_max=30, lam=1,
+                       boundary_conditions="loop", tau=9)
+    eng.close()
+
+
+# --------------------------------------------------------------------------- #
+# MBRL rollouts (config 5 shape): policy in the loop, K-shoot                 #
+# --------------------------------------------------------------------------- #
+
+def test_policy_rollout_graph_equals_eager_and_oracle():
+    _need_gpu()
+    from mbrl_traffic_b200.rollout import (BatchedMacroEnv, FeedForwardActor,
+                                           policy_rollout)
+    b, n, horizon = 96, 200, 11
+    obs = make_obs(b, n, seed=51)
+    m = make_model("arz", action_is_speed_limit=True)
+    env = BatchedMacroEnv(m, b, n, horizon=horizon)
+    torch.manual_seed(0)
+    actor = FeedForwardActor(2 * n).to("cuda:0")
+    x0 = gpu(obs)
+    eager = policy_rollout(env, actor, x0, use_graph=False).clone()
+    final_eager = env.obs.clone()
+    graphed = policy_rollout(env, actor, x0, use_graph=True).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(eager, graphed)
+    assert torch.equal(final_eager, env.obs)
+    # oracle: same actions (recomputed by the actor on the oracle's states)
+    cur, total = obs, np.zeros(b)
+    for _ in range(horizon):
+        with torch.no_grad():
+            act = actor(gpu(cur)).double().cpu().numpy()
+        cur = o.arz_step(cur, v_max=act)
+        total += o.mean_speed_reward(cur)
+    assert np.array_equal(env.obs.cpu().numpy(), cur)
+    np.testing.assert_allclose(eager.cpu().numpy(), total, rtol=1e-11)
+    m.close()
+
+
+def test_kshoot_picks_the_best_sampled_sequence():
+    _need_gpu()
+    from mbrl_traffic_b200.rollout import KShootPolicy
+    b, n, k, horizon = 5, 64, 6, 4
+    obs = make_obs(b, n, seed=52)
+    m = make_model("arz", action_is_speed_limit=True)
+    pol = KShootPolicy(m, b, n, num_particles=k, traj_length=horizon, seed=3)
+    actions = pol.sample_actions()
+    first, returns = pol.get_action(gpu(obs), actions)
+    torch.cuda.synchronize()
+    acts = actions.cpu().numpy()                       # (T, b*k)
+    ref = np.zeros((b, k))
+    for e in range(b):
+        for p in range(k):
+            cur = obs[e]
+            for t in range(horizon):
+                cur = o.arz_step(cur, v_max=float(acts[t, e * k + p]))
+                ref[e, p] += o.mean_speed_reward(cur)
+    np.testing.assert_allclose(returns.cpu().numpy(), ref, rtol=1e-11)
+    best = ref.argmax(axis=1)
+    expect = acts[0].reshape(b, k)[np.arange(b), best]
+    assert np.array_equal(first.cpu().numpy(), expect)
+    m.close()

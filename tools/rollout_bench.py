@@ -1,0 +1,71 @@
+"""Config 5: feed-forward policy driving a batched ARZ ensemble.
+
+    python tools/rollout_bench.py [--envs 4096] [--cells 1000] [--horizon 500]
+
+Reports road-steps/s and cell-updates/s of the whole loop (policy MLP +
+model step + reward), CUDA-graph replayed, and of K-shoot planning.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mbrl_traffic_b200 import ARZModel, ARZ_MODEL_PARAMS  # noqa: E402
+from mbrl_traffic_b200.rollout import (BatchedMacroEnv, FeedForwardActor,  # noqa: E402
+                                       KShootPolicy, policy_rollout)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs", type=int, default=4096)
+    ap.add_argument("--cells", type=int, default=1000)
+    ap.add_argument("--horizon", type=int, default=500)
+    ap.add_argument("--dtype", default="float64")
+    args = ap.parse_args()
+    tdt = torch.float64 if args.dtype == "float64" else torch.float32
+    b, n = args.envs, args.cells
+    p = dict(ARZ_MODEL_PARAMS)
+    p.pop("optimizer_cls")
+    model = ARZModel(None, None, None, None, 0, optimizer_cls=None,
+                     action_is_speed_limit=True, **p)
+    rng = np.random.default_rng(0)
+    rho = rng.uniform(0.05, 0.9, (b, n))
+    v = 30 * (1 - rho) + rng.normal(0, 1, (b, n))
+    obs = torch.as_tensor(np.concatenate((rho, v), 1), device="cuda").to(tdt)
+    env = BatchedMacroEnv(model, b, n, horizon=args.horizon, dtype=tdt)
+    actor = FeedForwardActor(2 * n).to("cuda")
+    out = {}
+    for graph in (False, True):
+        policy_rollout(env, actor, obs, horizon=8, use_graph=graph)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        total = policy_rollout(env, actor, obs, use_graph=graph)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out["graph" if graph else "eager"] = dict(
+            seconds=round(dt, 4), road_steps_per_s=b * args.horizon / dt,
+            cell_updates_per_s=b * n * args.horizon / dt,
+            mean_return=float(total.mean()))
+    k, h = 16, 10
+    pol = KShootPolicy(model, b // k, n, num_particles=k, traj_length=h, dtype=tdt)
+    pol.get_action(obs[:b // k])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        pol.get_action(obs[:b // k])
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 10
+    out["kshoot"] = dict(roads=b // k, particles=k, traj_length=h,
+                         plans_per_s=(b // k) / dt,
+                         cell_updates_per_s=b * n * h / dt)
+    print(json.dumps(dict(envs=b, cells=n, horizon=args.horizon,
+                          dtype=args.dtype, **out)))
+
+
+if __name__ == "__main__":
+    main()
