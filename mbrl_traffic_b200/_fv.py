@@ -208,6 +208,67 @@ class FiniteVolumeModel(Model):
         eng.density_sqerr(pred, t, sq)
         return float(sq.sum().item() / (n_envs * n_cells))
 
+    #: order of the fitted parameters in a candidate vector
+    _fit_names = ("rho_max", "v_max", "lam")
+
+    def population_loss(self, candidates, states, actions, next_states):
+        """``compute_loss`` for a whole population of parameter vectors in one
+        batched step: candidate ``p`` becomes the per-road parameters of its
+        own copy of the ``B`` rows (``P*B`` roads in one ``mt_step``).
+
+        ``candidates`` is ``(P, D)`` in the order of ``fitness_fn``'s ``x``
+        (lwr.py:149, arz.py:156).  Returns a NumPy array of ``P`` losses,
+        each equal to ``compute_loss`` with that candidate's parameters.
+        """
+        import torch
+        dev = "cuda:%d" % self.device
+        cand = np.asarray(candidates, dtype=np.float64)
+        arr = np.asarray(states.cpu() if _is_torch(states) else states)
+        if arr.dtype not in (np.float32, np.float64):
+            arr = arr.astype(np.float64)
+        tgt = np.asarray(next_states.cpu() if _is_torch(next_states) else next_states,
+                         dtype=arr.dtype)
+        p, b, n = cand.shape[0], arr.shape[0], arr.shape[1] // 2
+        tdt = torch.float64 if arr.dtype == np.float64 else torch.float32
+        s = torch.as_tensor(np.ascontiguousarray(arr), device=dev).repeat(p, 1)
+        t = torch.as_tensor(np.ascontiguousarray(tgt), device=dev).repeat(p, 1)
+        eng = Engine(self._engine_model, arr.dtype.name, p * b, n, device=self.device,
+                     max_n_eta=self._max_n_eta())
+        try:
+            kw = dict(dx=self.dx, dt=self.dt,
+                      boundary_conditions=self.boundary_conditions)
+            for name in self._param_names:
+                kw[name] = getattr(self, name)
+            kw.update(self._engine_kwargs())
+            for j, name in enumerate(self._fit_names):
+                kw[name] = torch.as_tensor(cand[:, j], device=dev).to(tdt) \
+                    .repeat_interleave(b).contiguous()
+            if "gamma" in kw and isinstance(kw["gamma"], np.ndarray):
+                kw["gamma"] = torch.as_tensor(kw["gamma"], device=dev).to(tdt)
+            eng.set_params(fast_math=self.fast_math, **kw)
+            pred = torch.empty_like(s)
+            eng.step(s, pred)
+            sq = torch.empty(p * b, dtype=tdt, device=dev)
+            eng.density_sqerr(pred, t, sq)
+            out = (sq.view(p, b).sum(dim=1) / (b * n)).double().cpu().numpy()
+        finally:
+            eng.close()
+        return out
+
+    def _make_optimizer(self, optimizer_cls, param_low, param_high, fitness_fn):
+        """Build the optimizer the way the reference does (lwr.py:180-186);
+        population optimizers of this package also get the batched scorer."""
+        if not callable(optimizer_cls):
+            return None
+        kw = dict(self.optimizer_params)
+        if getattr(optimizer_cls, "accepts_batch_fitness", False):
+            def batch_fitness(population):
+                states, actions, _, next_states, _ = self.replay_buffer.sample()
+                return self.population_loss(population, states, actions, next_states)
+            kw.setdefault("batch_fitness_fn", batch_fitness)
+        return optimizer_cls(param_low=param_low, param_high=param_high,
+                             fitness_fn=fitness_fn, verbose=self.verbose, **kw)
+
     # ------------------------------------------------------------------ #
     def close(self):
         """Release the engines (device memory)."""

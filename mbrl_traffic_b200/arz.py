@@ -29,6 +29,7 @@ class ARZModel(FiniteVolumeModel):
 
     _engine_model = "arz"
     _param_names = ("rho_max", "v_max", "lam", "tau")
+    _fit_names = ("rho_max", "v_max", "tau", "lam")      # arz.py:156
 
     def __init__(self,
                  sess,
@@ -80,15 +81,8 @@ class ARZModel(FiniteVolumeModel):
             return loss
 
         self._fitness_fn = fitness_fn
-        self.optimizer = None
-        if callable(optimizer_cls):
-            self.optimizer = optimizer_cls(
-                param_low=[0, 0, 0, 0],
-                param_high=[rho_max_max, v_max_max, tau_max, LAM_MAX],
-                fitness_fn=fitness_fn,
-                verbose=verbose,
-                **self.optimizer_params
-            )
+        self.optimizer = self._make_optimizer(
+            optimizer_cls, [0, 0, 0, 0], [rho_max_max, v_max_max, tau_max, LAM_MAX], fitness_fn)
 
         # critical density defined by the Green-shield Model (arz.py:199)
         self.rho_crit = self.rho_max / 2

@@ -102,13 +102,8 @@ class NonLocalModel(FiniteVolumeModel):
             return loss
 
         self._fitness_fn = fitness_fn
-        self.optimizer = None
-        if callable(optimizer_cls):
-            self.optimizer = optimizer_cls(
-                param_low=[0, 0, 0],
-                param_high=[rho_max_max, v_max_max, LAM_MAX],
-                fitness_fn=fitness_fn, verbose=verbose,
-                **self.optimizer_params)
+        self.optimizer = self._make_optimizer(
+            optimizer_cls, [0, 0, 0], [rho_max_max, v_max_max, LAM_MAX], fitness_fn)
 
     def weights(self):
         """The look-ahead weights gamma_k for the current eta / dx / kernel."""

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--cells", type=int, default=1000)
     ap.add_argument("--horizon", type=int, default=500)
     ap.add_argument("--dtype", default="float64")
+    ap.add_argument("--actor-dtype", default="bfloat16")
     args = ap.parse_args()
     tdt = torch.float64 if args.dtype == "float64" else torch.float32
     b, n = args.envs, args.cells
@@ -38,7 +39,7 @@ def main():
     v = 30 * (1 - rho) + rng.normal(0, 1, (b, n))
     obs = torch.as_tensor(np.concatenate((rho, v), 1), device="cuda").to(tdt)
     env = BatchedMacroEnv(model, b, n, horizon=args.horizon, dtype=tdt)
-    actor = FeedForwardActor(2 * n).to("cuda")
+    actor = FeedForwardActor(2 * n).to("cuda").to(getattr(torch, args.actor_dtype))
     out = {}
     for graph in (False, True):
         policy_rollout(env, actor, obs, horizon=8, use_graph=graph)
@@ -64,7 +65,7 @@ def main():
                          plans_per_s=(b // k) / dt,
                          cell_updates_per_s=b * n * h / dt)
     print(json.dumps(dict(envs=b, cells=n, horizon=args.horizon,
-                          dtype=args.dtype, **out)))
+                          dtype=args.dtype, actor_dtype=args.actor_dtype, **out)))
 
 
 if __name__ == "__main__":
