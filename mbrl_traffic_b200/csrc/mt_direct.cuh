@@ -165,11 +165,13 @@ __global__ void __launch_bounds__(MAX_BLOCK, 2) step_vec_kernel(const StepArgs<T
     if (ARZ) {
       e.qc = A::mul(e.rho_crit, A::mul(e.v_max, e.g_crit));
       unpack(__ldg(reinterpret_cast<const VT*>(row + N) + w.vec), v);
-      arz_pass1<T, FAST, LAMK, V>(e, rho, v, y, r, D, S);
-      xR[w.xi + 1] = r[V - 1];
-    } else {
-      lwr_pass1<T, FAST, LAMK, V>(e, rho, D, S);
     }
+    with_lam<LAMK>(e.flags, [&](auto kind) {
+      constexpr int K = decltype(kind)::value;
+      if (ARZ) arz_pass1<T, FAST, K, V>(e, rho, v, y, r, D, S);
+      else lwr_pass1<T, FAST, K, V>(e, rho, D, S);
+    });
+    if (ARZ) xR[w.xi + 1] = r[V - 1];
     xS[w.xi] = S[0];
     xD[w.xi + 1] = D[V - 1];
     if (row_last) xS[w.xi + 1] = S[V - 1];
@@ -179,31 +181,34 @@ __global__ void __launch_bounds__(MAX_BLOCK, 2) step_vec_kernel(const StepArgs<T
   T num = 0, den = 0;
   if (w.active) {
     T S_right = xS[w.xi + 1], D_left = xD[w.xi], r_left = xR[w.xi];
-    // tile edges of a multi-tile row: re-derive the halo cell from global memory
-    if (w.tile_last && !row_last) {
-      const int j = (w.vec + 1) * V;
-      T yy, rr, dd;
-      if (ARZ) arz_cell<T, FAST, LAMK>(e, __ldg(row + j), __ldg(row + N + j), yy, rr, dd, S_right);
-      else lwr_cell<T, FAST, LAMK>(e, __ldg(row + j), dd, S_right);
-    }
-    if (w.tile_first && !row_first) {
-      const int j = w.vec * V - 1;
-      T yy, ss;
-      if (ARZ) arz_cell<T, FAST, LAMK>(e, __ldg(row + j), __ldg(row + N + j), yy, r_left, D_left, ss);
-      else lwr_cell<T, FAST, LAMK>(e, __ldg(row + j), D_left, ss);
-    }
     T loop_a = 0, loop_b = 0;
     if (row_first && a.bc.bc_l == MT_BC_LOOP) {
       if (ARZ) { loop_a = __ldg(row + N - 1); loop_b = __ldg(row + 2 * N - 1); }
       else { loop_a = __ldg(row + N - 2); loop_b = __ldg(row + N - 1); }
     }
     T rn[V], vn[V];
-    if (ARZ)
-      arz_pass2<T, FAST, LAMK, V>(e, a.bc, row_first, row_last, rho, v, y, r, D, S, S_right,
-                                  D_left, r_left, loop_a, loop_b, rn, vn);
-    else
-      lwr_pass2<T, FAST, LAMK, V>(e, a.bc, row_first, row_last, rho, D, S, S_right, D_left,
-                                  loop_a, loop_b, rn, vn);
+    with_lam<LAMK>(e.flags, [&](auto kind) {
+      constexpr int K = decltype(kind)::value;
+      // tile edges of a multi-tile row: re-derive the halo cell from global memory
+      if (w.tile_last && !row_last) {
+        const int j = (w.vec + 1) * V;
+        T yy, rr, dd;
+        if (ARZ) arz_cell<T, FAST, K>(e, __ldg(row + j), __ldg(row + N + j), yy, rr, dd, S_right);
+        else lwr_cell<T, FAST, K>(e, __ldg(row + j), dd, S_right);
+      }
+      if (w.tile_first && !row_first) {
+        const int j = w.vec * V - 1;
+        T yy, ss;
+        if (ARZ) arz_cell<T, FAST, K>(e, __ldg(row + j), __ldg(row + N + j), yy, r_left, D_left, ss);
+        else lwr_cell<T, FAST, K>(e, __ldg(row + j), D_left, ss);
+      }
+      if (ARZ)
+        arz_pass2<T, FAST, K, V>(e, a.bc, row_first, row_last, rho, v, y, r, D, S, S_right,
+                                 D_left, r_left, loop_a, loop_b, rn, vn);
+      else
+        lwr_pass2<T, FAST, K, V>(e, a.bc, row_first, row_last, rho, D, S, S_right, D_left,
+                                 loop_a, loop_b, rn, vn);
+    });
     if (want_reward) {
 #pragma unroll
       for (int k = 0; k < V; ++k) { num += rn[k] * vn[k]; den += rn[k]; }

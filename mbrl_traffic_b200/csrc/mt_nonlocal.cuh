@@ -193,8 +193,13 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) nonlocal_pipe_kernel(c
 #pragma unroll
         for (int k = 0; k < V; ++k) rho[u * V + k] = tmp[k];
       }
+      T ghost_v = T(0);   // V(rho_R) for a CONSTANT downstream end
+      with_lam<LAMK>(e.flags, [&](auto kind) {
+        constexpr int K = decltype(kind)::value;
 #pragma unroll
-      for (int k = 0; k < CPT; ++k) mine[k] = v_eq<T, FAST, LAMK>(rho[k], e);
+        for (int k = 0; k < CPT; ++k) mine[k] = v_eq<T, FAST, K>(rho[k], e);
+        if (row_last && a.bc.bc_r == MT_BC_CONSTANT) ghost_v = v_eq<T, FAST, K>(a.bc.br0, e);
+      });
 #pragma unroll
       for (int k = 0; k < CPT; ++k) ve[ve_row + k * VSTR] = mine[k];
       // downstream ghosts V(rho_{N+c}), c < n_eta: cell N+c sits in plane
@@ -204,8 +209,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) nonlocal_pipe_kernel(c
         for (int k = 0; k < CPT; ++k)
           if (j0 + k < n_eta) ve[ve_row + k * VSTR + a.nthr] = mine[k];
       } else if (row_last) {
-        const T g = (a.bc.bc_r == MT_BC_CONSTANT) ? v_eq<T, FAST, LAMK>(a.bc.br0, e)
-                                                   : mine[CPT - 1];
+        const T g = (a.bc.bc_r == MT_BC_CONSTANT) ? ghost_v : mine[CPT - 1];
         T* blk = ve + el * (CPT * VSTR);
         for (int c = 0; c < n_eta; ++c) blk[(c % CPT) * VSTR + a.nthr + c / CPT] = g;
       }
@@ -244,8 +248,11 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) nonlocal_pipe_kernel(c
         rn[k] = A::sub(rho[k], A::mul(e.step, A::sub(F, Fm)));
         Fm = F;
       }
+      with_lam<LAMK>(e.flags, [&](auto kind) {
+        constexpr int K = decltype(kind)::value;
 #pragma unroll
-      for (int k = 0; k < CPT; ++k) vn[k] = v_eq<T, FAST, LAMK>(rn[k], e);
+        for (int k = 0; k < CPT; ++k) vn[k] = v_eq<T, FAST, K>(rn[k], e);
+      });
       if (want_reward) {
 #pragma unroll
         for (int k = 0; k < CPT; ++k) { num += rn[k] * vn[k]; den += rn[k]; }

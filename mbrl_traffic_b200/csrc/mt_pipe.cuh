@@ -376,12 +376,12 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
         if (ARZ) { loop_a = row[N - 1]; loop_b = row[2 * N - 1]; }
         else { loop_a = row[N - 2]; loop_b = row[N - 1]; }
       }
-      if (ARZ) {
-        arz_pass1<T, FAST, LAMK, CPT>(e, rho, v, y, r, D, S);
-        xR[xi + 1] = r[CPT - 1];
-      } else {
-        lwr_pass1<T, FAST, LAMK, CPT>(e, rho, D, S);
-      }
+      with_lam<LAMK>(e.flags, [&](auto kind) {
+        constexpr int K = decltype(kind)::value;
+        if (ARZ) arz_pass1<T, FAST, K, CPT>(e, rho, v, y, r, D, S);
+        else lwr_pass1<T, FAST, K, CPT>(e, rho, D, S);
+      });
+      if (ARZ) xR[xi + 1] = r[CPT - 1];
       xS[xi] = S[0];
       xD[xi + 1] = D[CPT - 1];
       if (row_last) xS[xi + 1] = S[CPT - 1];  // arz.py:405 / lwr.py:294
@@ -393,12 +393,16 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
     T num = 0, den = 0;
     if (active) {
       T rn[CPT], vn[CPT];
-      if (ARZ)
-        arz_pass2<T, FAST, LAMK, CPT>(e, a.bc, row_first, row_last, rho, v, y, r, D, S,
-                                      xS[xi + 1], xD[xi], xR[xi], loop_a, loop_b, rn, vn);
-      else
-        lwr_pass2<T, FAST, LAMK, CPT>(e, a.bc, row_first, row_last, rho, D, S, xS[xi + 1],
-                                      xD[xi], loop_a, loop_b, rn, vn);
+      const T S_right = xS[xi + 1], D_left = xD[xi], r_left = ARZ ? xR[xi] : T(0);
+      with_lam<LAMK>(e.flags, [&](auto kind) {
+        constexpr int K = decltype(kind)::value;
+        if (ARZ)
+          arz_pass2<T, FAST, K, CPT>(e, a.bc, row_first, row_last, rho, v, y, r, D, S, S_right,
+                                     D_left, r_left, loop_a, loop_b, rn, vn);
+        else
+          lwr_pass2<T, FAST, K, CPT>(e, a.bc, row_first, row_last, rho, D, S, S_right, D_left,
+                                     loop_a, loop_b, rn, vn);
+      });
       if (want_reward) {
 #pragma unroll
         for (int k = 0; k < CPT; ++k) { num += rn[k] * vn[k]; den += rn[k]; }

@@ -14,6 +14,7 @@
 #include "mt_math.cuh"
 #include "mt_pipe.cuh"
 #include "mt_ring.cuh"
+#include "mt_seg.cuh"
 #include "mt_direct.cuh"
 #include "mt_nonlocal.cuh"
 
@@ -429,6 +430,38 @@ int step_nonlocal(mt_engine* e, const T* obs_in, const T* action, T* obs_out, T*
   return MT_OK;
 }
 
+// ---- long roads: segment-pipelined kernel --------------------------------------
+template <typename T, int MODEL, bool FAST, int LAMK, bool UNIFORM, int U>
+int launch_seg(const SegArgs<T>& sa, int grid, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(step_seg_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(SegSmem<T, U>)));
+    configured = true;
+  }
+  return launch_pdl(step_seg_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>, sa, grid, sa.nc + 32,
+                    sizeof(SegSmem<T, U>), stream);
+}
+
+// the reference defaults (scalar parameters, lam == 1, rho_max == 1) get the
+// compile-time specialisation; everything else reads the per-road table
+template <typename T, int MODEL, bool FAST, int U>
+int launch_seg_spec(const SegArgs<T>& sa, int grid, bool uniform, int lamk, cudaStream_t s) {
+  if (uniform && lamk == LAM_ONE && sa.u.rho_max == T(1))
+    return launch_seg<T, MODEL, FAST, LAM_ONE_RM1, true, U>(sa, grid, s);
+  return launch_seg<T, MODEL, FAST, LAM_RUNTIME, false, U>(sa, grid, s);
+}
+
+template <typename T, int MODEL, int U>
+int launch_seg_fast(const SegArgs<T>& sa, int grid, bool fast, bool uniform, int lamk,
+                    cudaStream_t s) {
+  if constexpr (FastAllowed<T>::value) {
+    if (fast) return launch_seg_spec<T, MODEL, true, U>(sa, grid, uniform, lamk, s);
+  }
+  return launch_seg_spec<T, MODEL, false, U>(sa, grid, uniform, lamk, s);
+}
+
 // Steps roads [env0, env0 + n_env) of the batch; all pointers address the
 // whole batch (road 0) and are offset here.
 template <typename T>
@@ -503,6 +536,44 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     return MT_OK;
+  }
+
+  if (g.vector_ok && g.tiles > 1 && !(p.flags & MT_FLAG_NO_PIPELINE) && B <= 0x7fffffffLL) {
+    // a road longer than one tile: segments of it flow through the pipeline
+    int U = pipe_vectors_per_thread();
+    if (U == 0) U = (sizeof(T) == 8) ? 2 : 1;
+    if (N % (U * V) != 0) U = 1;
+    SegArgs<T> sa;
+    sa.in = obs_in; sa.out = obs_out; sa.table = table; sa.flags = flags; sa.action = action;
+    sa.partial = rew ? partial : nullptr;
+    sa.B = (int)B; sa.N = N;
+    sa.nc = PIPE_BLOCK / U;
+    const int seg_cells = sa.nc * U * V;
+    sa.tiles_per_row = (N + seg_cells - 1) / seg_cells;
+    const long long n_tiles = B * (long long)sa.tiles_per_row;
+    if (n_tiles <= 0x7fffffffLL && sa.tiles_per_row <= e->max_tiles) {
+      sa.n_tiles = (int)n_tiles;
+      sa.bc = bc; sa.step = step; sa.u = uniform_of<T>(e);
+      const long long slots = 2LL * e->sm_count;
+      const int grid = (int)(n_tiles < slots ? n_tiles : slots);
+      int rc;
+      if (e->cfg.model == MT_MODEL_ARZ)
+        rc = U == 2 ? launch_seg_fast<T, 1, 2>(sa, grid, fast, e->uniform, e->lamk, stream)
+                    : launch_seg_fast<T, 1, 1>(sa, grid, fast, e->uniform, e->lamk, stream);
+      else
+        rc = U == 2 ? launch_seg_fast<T, 0, 2>(sa, grid, fast, e->uniform, e->lamk, stream)
+                    : launch_seg_fast<T, 0, 1>(sa, grid, fast, e->uniform, e->lamk, stream);
+      if (rc != MT_OK) return rc;
+      e->launches++;
+      if (rew) {
+        const int wpb = 8;
+        reward_finalize_kernel<T><<<(unsigned)((B + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+            (const T*)partial, reward_out, B, sa.tiles_per_row);
+        e->launches++;
+      }
+      CUDA_TRY(cudaGetLastError());
+      return MT_OK;
+    }
   }
 
   StepArgs<T> a;

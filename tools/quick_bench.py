@@ -34,6 +34,8 @@ def main():
     ap.add_argument("--reward", action="store_true")
     ap.add_argument("--direct", action="store_true")
     ap.add_argument("--n-eta", type=int, default=16)
+    ap.add_argument("--per-env", action="store_true",
+                    help="pass the parameters as per-road device arrays")
     ap.add_argument("--rho-max", type=float, default=1.0)
     args = ap.parse_args()
 
@@ -45,8 +47,12 @@ def main():
         from mbrl_traffic_b200.nonlocal_ import lookahead_weights
         gamma = torch.as_tensor(lookahead_weights(50.0 * args.n_eta, 50.0),
                                 device="cuda").to(tdt)
-    eng.set_params(dx=50, dt=0.5, rho_max=args.rho_max, v_max=30, lam=1,
-                   boundary_conditions="loop", tau=9, fast_math=args.fast,
+    def par(x):
+        if not args.per_env:
+            return x
+        return torch.full((b,), float(x), dtype=tdt, device="cuda")
+    eng.set_params(dx=50, dt=0.5, rho_max=par(args.rho_max), v_max=par(30), lam=par(1),
+                   boundary_conditions="loop", tau=par(9), fast_math=args.fast,
                    no_pipeline=args.direct, gamma=gamma)
     rng = np.random.default_rng(0)
     rho = args.rho_max * rng.uniform(0.05, 0.9, (b, n))
