@@ -829,9 +829,15 @@ int mt_step_host(mt_engine* e, const void* obs_in_host, const void* action_host,
   // Roads are independent, so the batch is cut into chunks that flow through
   // upload -> n_steps kernels -> download on NS streams: PCIe carries both
   // directions at once and the kernels hide behind the copies.
-  long long n_chunks = (B * (long long)row_bytes) / (8u << 20);  // ~8 MB per chunk
+  static long long chunk_bytes = 0;
+  if (chunk_bytes == 0) {
+    const char* s = getenv("MT_HOST_CHUNK_MB");
+    chunk_bytes = (long long)((s ? atof(s) : 8.0) * (1 << 20));
+    if (chunk_bytes < (1 << 16)) chunk_bytes = 1 << 16;
+  }
+  long long n_chunks = (B * (long long)row_bytes) / chunk_bytes;
   if (n_chunks < 1) n_chunks = 1;
-  if (n_chunks > 16) n_chunks = 16;
+  if (n_chunks > 64) n_chunks = 64;
   if (n_chunks > B) n_chunks = B;
   const long long per = (B + n_chunks - 1) / n_chunks;
   for (int i = 0; i < NS; ++i) CUDA_TRY(cudaStreamWaitEvent(e->hs[i], e->params_ready, 0));
