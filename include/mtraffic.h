@@ -157,6 +157,19 @@ int mt_step_host(mt_engine *e, const void *obs_in_host,
 int mt_density_sqerr(mt_engine *e, const void *obs_pred,
                      const void *obs_target, void *out_per_env, void *stream);
 
+/* Microscopic -> macroscopic aggregation (the reference's notebook loop,
+ * experiments/plotting_results.ipynb cell 8): records (time, position, speed)
+ * -> per (time row, section) mean speed and density.  All pointers are DEVICE
+ * float64; records must be grouped by non-decreasing time row (MT_EINVAL
+ * otherwise); scratch_idx holds 2*n_records int32.  Bit-equal to the
+ * reference's sequential accumulation.  Synchronises the stream once (to
+ * read the sortedness flag). */
+int mt_aggregate(const void *time, const void *position, const void *speed,
+                 int64_t n_records, double dt, double dx, int32_t n_rows,
+                 int32_t n_sections, double empty_speed, void *scratch_idx,
+                 void *speed_out, void *density_out, int32_t device,
+                 void *stream);
+
 /* Number of kernels this engine has launched so far. */
 int mt_launch_count(const mt_engine *e, int64_t *out);
 

@@ -22,7 +22,7 @@ MT_FLAG_NO_PIPELINE = 2
 EXPORTS = (
     "mt_version", "mt_last_error", "mt_create", "mt_destroy", "mt_set_params",
     "mt_step", "mt_rollout", "mt_step_host", "mt_density_sqerr",
-    "mt_launch_count", "mt_alloc_pinned", "mt_free_pinned",
+    "mt_launch_count", "mt_alloc_pinned", "mt_free_pinned", "mt_aggregate",
 )
 
 
@@ -94,6 +94,9 @@ def load():
     lib.mt_step_host.argtypes = [vp, vp, vp, vp, vp, i32]
     lib.mt_density_sqerr.restype = ctypes.c_int
     lib.mt_density_sqerr.argtypes = [vp, vp, vp, vp, vp]
+    lib.mt_aggregate.restype = ctypes.c_int
+    lib.mt_aggregate.argtypes = [vp, vp, vp, i64, ctypes.c_double, ctypes.c_double,
+                                 i32, i32, ctypes.c_double, vp, vp, vp, i32, vp]
     lib.mt_launch_count.restype = ctypes.c_int
     lib.mt_launch_count.argtypes = [vp, ctypes.POINTER(i64)]
     lib.mt_alloc_pinned.restype = ctypes.c_int

@@ -12,8 +12,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SOURCES = [os.path.join(HERE, "csrc", "mtraffic.cu")]
-HEADERS = [os.path.join(HERE, "csrc", "mt_math.cuh"),
-           os.path.join(ROOT, "include", "mtraffic.h")]
+HEADERS = sorted(
+    os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))
+    if f.endswith((".cuh", ".h"))) + [os.path.join(ROOT, "include", "mtraffic.h")]
 OUTPUT = os.path.join(HERE, "libmtraffic.so")
 
 NVCC_FLAGS = [

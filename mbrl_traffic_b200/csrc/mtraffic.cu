@@ -17,6 +17,7 @@
 #include "mt_seg.cuh"
 #include "mt_direct.cuh"
 #include "mt_nonlocal.cuh"
+#include "mt_aggregate.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -894,6 +895,46 @@ int mt_density_sqerr(mt_engine* e, const void* obs_pred, const void* obs_target,
         (const float*)obs_pred, (const float*)obs_target, (float*)out_per_env, B, N);
   e->launches++;
   CUDA_TRY(cudaGetLastError());
+  return MT_OK;
+}
+
+int mt_aggregate(const void* time, const void* position, const void* speed, int64_t n_records,
+                 double dt, double dx, int32_t n_rows, int32_t n_sections, double empty_speed,
+                 void* scratch_idx, void* speed_out, void* density_out, int32_t device,
+                 void* stream) {
+  if (!time || !position || !speed || !scratch_idx || !speed_out || !density_out)
+    return fail(MT_EINVAL, "mt_aggregate: NULL argument");
+  if (n_records < 0 || n_rows < 1 || n_sections < 1 || !(dt > 0) || !(dx > 0))
+    return fail(MT_EINVAL, "mt_aggregate: bad shape or step");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t s = (cudaStream_t)stream;
+  int* flag = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&flag, sizeof(int)));
+  cudaError_t err = cudaMemsetAsync(flag, 0, sizeof(int), s);
+  AggArgs a;
+  a.time = (const double*)time; a.pos = (const double*)position; a.speed = (const double*)speed;
+  a.t_idx = (int*)scratch_idx; a.x_idx = (int*)scratch_idx + n_records;
+  a.M = n_records; a.dt = dt; a.dx = dx; a.empty_speed = empty_speed;
+  a.n_rows = n_rows; a.n_sections = n_sections;
+  a.speed_out = (double*)speed_out; a.density_out = (double*)density_out;
+  a.unsorted = flag;
+  int unsorted = 0;
+  if (err == cudaSuccess && n_records > 0) {
+    const int block = 256;
+    const unsigned grid = (unsigned)((n_records + block - 1) / block);
+    agg_index_kernel<<<grid, block, 0, s>>>(a);
+    agg_check_sorted_kernel<<<grid, block, 0, s>>>(a);
+  }
+  if (err == cudaSuccess)
+    err = cudaMemcpyAsync(&unsorted, flag, sizeof(int), cudaMemcpyDeviceToHost, s);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(s);
+  if (err == cudaSuccess && !unsorted) {
+    agg_reduce_kernel<<<(unsigned)n_rows, 128, 0, s>>>(a);
+    err = cudaGetLastError();
+  }
+  cudaFree(flag);
+  if (err != cudaSuccess) return fail(MT_ECUDA, "mt_aggregate: %s", cudaGetErrorString(err));
+  if (unsorted) return fail(MT_EINVAL, "mt_aggregate: records must be grouped by non-decreasing time row");
   return MT_OK;
 }
 

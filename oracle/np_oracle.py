@@ -358,3 +358,25 @@ def mean_speed_reward(obs):
     rho, v, squeeze = _split(obs)
     r = (rho * v).sum(axis=1) / rho.sum(axis=1)
     return r[0] if squeeze else r
+
+
+def aggregate_micro(time, position, speed, dx=50.0, dt=0.5, length=1500.0,
+                    total_time=1800.0, empty_speed=30.0):
+    """Micro -> macro aggregation exactly as the reference's notebook loop
+    (experiments/plotting_results.ipynb cell 8), record by record."""
+    import math
+    n_rows, n_sec = int(round(total_time / dt)) + 1, int(round(length / dx))
+    speeds = np.zeros((n_rows, n_sec))
+    num = np.zeros((n_rows, n_sec))
+    for t, x, v in zip(time, position, speed):
+        ix, iy = math.floor(float(t) / dt), math.floor(float(x) / dx)
+        try:
+            speeds[ix, iy] += float(v)
+            num[ix, iy] += 1
+        except IndexError:
+            pass
+    dens = num / dx
+    speeds[num == 0] = empty_speed
+    safe = num.copy()
+    safe[safe == 0] = 1
+    return speeds / safe, dens

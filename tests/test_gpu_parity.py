@@ -873,3 +873,35 @@ def test_cem_recovers_model_parameters_from_data():
     pred = m.get_next_obs(obs, None)
     assert abs(o.density_mse(nxt, pred) - err) <= 1e-9 * err
     m.close()
+
+
+# --------------------------------------------------------------------------- #
+# micro -> macro aggregation                             #
+# --------------------------------------------------------------------------- #
+
+@pytest.mark.parametrize("sorted_input", [True, False])
+def test_aggregate_micro_is_bit_equal_to_the_notebook_loop(sorted_input):
+    _need_gpu()
+    from mbrl_traffic_b200.aggregate import aggregate_micro, macro_observations
+    rng = np.random.default_rng(71)
+    n_veh, n_t = 57, 40
+    t = np.repeat(np.arange(n_t) * 0.5, n_veh)
+    x = rng.uniform(-60, 1560, t.size)          # a few records off both ends
+    v = rng.uniform(0, 30, t.size)
+    t[5] = 21.0                                  # past the last row: dropped
+    if not sorted_input:
+        perm = rng.permutation(t.size)
+        t, x, v = t[perm], x[perm], v[perm]
+    kw = dict(dx=50.0, dt=0.5, length=1500.0, total_time=19.5)
+    ref_s, ref_d = o.aggregate_micro(t, x, v, **kw)
+    s, d = aggregate_micro(t, x, v, **kw)
+    if sorted_input:
+        assert np.array_equal(s.cpu().numpy(), ref_s)
+    else:
+        # a stable sort keeps each bin's record order only for ties in time;
+        # shuffled input changes the summation order -> rounding-level change
+        np.testing.assert_allclose(s.cpu().numpy(), ref_s, rtol=1e-14)
+    assert np.array_equal(d.cpu().numpy(), ref_d)
+    assert (ref_d == 0).any() and (s.cpu().numpy()[ref_d == 0] == 30).all()
+    obs = macro_observations(s, d)
+    assert obs.shape == (40, 60)
