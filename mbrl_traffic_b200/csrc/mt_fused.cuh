@@ -1,0 +1,282 @@
+// mt_fused.cuh -- multi-step rollouts in ONE launch.
+//
+// Same producer/consumer pipeline as mt_pipe.cuh, but every tile visit
+// advances its roads by a.n_inner model steps: the state stays in registers
+// between steps, only the three edge values (and, for the LOOP rule, the old
+// boundary-source cells, which travel in the road's pad slots of the exchange
+// arrays) cross threads, at one named barrier per step.  HBM sees each road
+// once per rollout instead of once per step, so the loop of
+// experiments/evaluate_model.py:398-403 (and any rollout without a policy in
+// the loop) runs at the arithmetic rate of the chip instead of the bandwidth
+// rate.  Per-step speed limits are read as they are needed
+// (action[j * stride + road]); a reward is produced for the final step only.
+// Kept apart from step_pipe_kernel so that the single-step kernel's code and
+// register allocation stay exactly as tuned.
+#pragma once
+#include <stdint.h>
+#include "mtraffic.h"
+#include "mt_math.cuh"
+#include "mt_cell.cuh"
+#include "mt_pipe.cuh"
+
+namespace mt {
+
+template <typename T, int MODEL, bool FAST, int LAMK, bool UNIFORM, int U>
+__global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_fused_kernel(const PipeArgs<T> a) {
+  constexpr int V = Vec<T>::N;
+  constexpr int CPT = U * V;
+  constexpr bool ARZ = (MODEL == 1);
+  constexpr int PIPE_STAGES = PipeCfg<T, U>::STAGES;
+  constexpr int PIPE_XCH = PipeCfg<T, U>::XCH;
+  using A = Ar<T, FAST>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  PipeSmem<T, U>& sm = *reinterpret_cast<PipeSmem<T, U>*>(smem_raw);
+
+  const int t = threadIdx.x;
+  const int NC = a.nc;
+  const int N = a.N;
+  const uint32_t row_bytes = 2u * (uint32_t)N * (uint32_t)sizeof(T);
+  const uint32_t tile_bytes = (uint32_t)a.epc * row_bytes;
+  const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int last_tile = a.n_tiles - 1;
+  const int last_envs = a.B - last_tile * a.epc;  // roads in the (ragged) last tile
+
+  const uint32_t in0 = smem_u32(sm.in[0]), out0 = smem_u32(sm.out[0]);
+  const uint32_t full0 = smem_u32(&sm.full[0]), empty0 = smem_u32(&sm.empty[0]);
+  const uint32_t ofull0 = smem_u32(&sm.out_full[0]), ofree0 = smem_u32(&sm.out_free[0]);
+
+  pdl_launch_dependents();
+  // pad slots of the exchange arrays stay zero for the kernel's life: they
+  // feed the (discarded) left-face flux of each road's first cell
+  for (int i = t; i < 2 * PIPE_XCH; i += blockDim.x) { (&sm.xD[0][0])[i] = T(0); (&sm.xR[0][0])[i] = T(0); }
+  if (t == 0) {
+    for (int s = 0; s < PIPE_STAGES; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], (uint32_t)(NC >> 5));
+    }
+    for (int o = 0; o < PIPE_OUT; ++o) {
+      mbar_init(&sm.out_full[o], (uint32_t)(NC >> 5));
+      mbar_init(&sm.out_free[o], 1);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_wait_prior_grid();  // everything above overlapped the previous kernel's tail
+
+  // ======================= producer warp ===================================
+  if (t >= NC) {
+    if (t == NC) {
+      const unsigned char* gin = reinterpret_cast<const unsigned char*>(a.in);
+      unsigned char* gout = reinterpret_cast<unsigned char*>(a.out);
+      auto bytes_of = [&](int tile) -> uint32_t {
+        return tile == last_tile ? (uint32_t)last_envs * row_bytes : tile_bytes;
+      };
+      auto issue_load = [&](int i) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int s = i % PIPE_STAGES;
+        if (ARZ) {
+          const uint32_t bytes = bytes_of(tile);
+          mbar_expect_tx(full0 + 8 * s, bytes);
+          bulk_load(in0 + (uint32_t)s * PIPE_TILE_BYTES, gin + (size_t)tile * tile_bytes, bytes,
+                    full0 + 8 * s);
+        } else {
+          // LWR ignores the input velocity (lwr.py:197): fetch the density half
+          // of each road only, at its usual place in the stage
+          const int envs = tile == last_tile ? last_envs : a.epc;
+          const uint32_t half = row_bytes >> 1;
+          mbar_expect_tx(full0 + 8 * s, (uint32_t)envs * half);
+          for (int r = 0; r < envs; ++r)
+            bulk_load(in0 + (uint32_t)s * PIPE_TILE_BYTES + (uint32_t)r * row_bytes,
+                      gin + (size_t)tile * tile_bytes + (size_t)r * row_bytes, half,
+                      full0 + 8 * s);
+        }
+      };
+      auto prefetch = [&](int i) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        if (ARZ) {
+          bulk_prefetch_l2(gin + (size_t)tile * tile_bytes, bytes_of(tile));
+        } else {
+          const int envs = tile == last_tile ? last_envs : a.epc;
+          for (int r = 0; r < envs; ++r)
+            bulk_prefetch_l2(gin + (size_t)tile * tile_bytes + (size_t)r * row_bytes,
+                             row_bytes >> 1);
+        }
+      };
+      const int pre = n_my < PIPE_STAGES ? n_my : PIPE_STAGES;
+      for (int i = 0; i < pre; ++i) issue_load(i);
+      const int ahead = a.l2_ahead;
+      for (int i = PIPE_STAGES; i < PIPE_STAGES + ahead && i < n_my; ++i) prefetch(i);
+      for (int i = 0; i < n_my; ++i) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int s = i % PIPE_STAGES, o = i % PIPE_OUT;
+        if (ahead > 0 && i + PIPE_STAGES + ahead < n_my) prefetch(i + PIPE_STAGES + ahead);
+        if (i + PIPE_STAGES < n_my) {  // refill stage s once the consumers have read tile i
+          mbar_wait_relaxed(empty0 + 8 * s, (uint32_t)((i / PIPE_STAGES) & 1), PRODUCER_NAP_NS);
+          issue_load(i + PIPE_STAGES);
+        }
+        mbar_wait_relaxed(ofull0 + 8 * o, (uint32_t)((i / PIPE_OUT) & 1), PRODUCER_NAP_NS);
+        bulk_store(gout + (size_t)tile * tile_bytes, out0 + (uint32_t)o * PIPE_TILE_BYTES,
+                   bytes_of(tile));
+        bulk_commit();
+        // all but the newest PIPE_OUT-1 stores have finished reading shared memory
+        bulk_wait_read<PIPE_OUT - 1>();
+        if (i >= PIPE_OUT - 1) mbar_arrive(ofree0 + 8 * ((i - (PIPE_OUT - 1)) % PIPE_OUT));
+      }
+      bulk_wait_read<0>();  // shared memory must outlive the last bulk store
+    }
+    return;
+  }
+
+  // ======================= consumers =======================================
+  // thread -> (road in tile, position in road); fixed for the kernel's life
+  const int el = t / a.tpe;
+  const int pos = t - el * a.tpe;
+  const bool row_first = (pos == 0), row_last = (pos == a.nthr - 1);
+  const bool owns_cells = (pos < a.nthr) && (el < a.epc);
+  const int xi = t + el;  // exchange slot (one pad slot per road)
+  const bool lane0 = (t & 31) == 0;
+  const bool want_reward = a.reward != nullptr;
+  // byte offsets of my first rho vector inside a stage, and of the v block
+  const uint32_t my_off = (uint32_t)el * row_bytes + (uint32_t)pos * (U * 16);
+  const uint32_t v_off = (uint32_t)N * (uint32_t)sizeof(T);
+
+  EnvC<T> e;
+  if (UNIFORM) {
+    load_uniform(e, a.u, 0, (const T*)nullptr, a.step);
+    if (ARZ) e.qc = A::mul(e.rho_crit, A::mul(e.v_max, e.g_crit));
+  }
+
+  int s = 0, o = 0, xpar = 0;
+  uint32_t ph_in = 0, ph_out = 0;
+  const int n_inner = a.n_inner;
+  for (int i = 0; i < n_my; ++i) {
+    const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+    const int envs_here = tile == last_tile ? last_envs : a.epc;
+    const int env = tile * a.epc + el;
+    const bool active = owns_cells && (el < envs_here);
+
+    if (active && !UNIFORM) {
+      // per-road constants: issued before the wait so the loads overlap it
+      load_env(e, a.table, a.flags, env, (const T*)nullptr, a.step);
+      if (ARZ) e.qc = A::mul(e.rho_crit, A::mul(e.v_max, e.g_crit));
+    }
+
+    mbar_wait(full0 + 8 * s, ph_in);
+
+    T rho[CPT], v[CPT], y[CPT], r[CPT], D[CPT], S[CPT];
+    if (active) {
+      const uint32_t src = in0 + (uint32_t)s * PIPE_TILE_BYTES + my_off;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        T tmp[V];
+        lds16(src + 16 * u, tmp);
+#pragma unroll
+        for (int k = 0; k < V; ++k) rho[u * V + k] = tmp[k];
+        if (ARZ) {
+          lds16(src + v_off + 16 * u, tmp);
+#pragma unroll
+          for (int k = 0; k < V; ++k) v[u * V + k] = tmp[k];
+        }
+      }
+    }
+
+    T num = 0, den = 0;
+    // n_inner model steps on this tile; between them the state lives in
+    // registers and only the edge values cross threads
+    for (int j = 0; j < n_inner; ++j) {
+      const bool last = (j == n_inner - 1);
+      T* const xS = sm.xS[xpar];
+      T* const xD = sm.xD[xpar];
+      T* const xR = sm.xR[xpar];
+      xpar ^= 1;
+      if (active) {
+        if (a.action != nullptr) {   // this step's speed limit for my road
+          e.v_max = __ldg(a.action + (size_t)j * a.action_stride + env);
+          if (ARZ) e.qc = A::mul(e.rho_crit, A::mul(e.v_max, e.g_crit));
+        }
+        with_lam<LAMK>(e.flags, [&](auto kind) {
+          constexpr int K = decltype(kind)::value;
+          if (ARZ) arz_pass1<T, FAST, K, CPT>(e, rho, v, y, r, D, S);
+          else lwr_pass1<T, FAST, K, CPT>(e, rho, D, S);
+        });
+        if (ARZ) xR[xi + 1] = r[CPT - 1];
+        xS[xi] = S[0];
+        xD[xi + 1] = D[CPT - 1];
+        if (row_last) {
+          xS[xi + 1] = S[CPT - 1];  // arz.py:405 / lwr.py:294
+          // OLD boundary-source cells for the LOOP rule of the road's first
+          // thread travel in the road's pad slots (whose flux is discarded)
+          xD[xi - pos] = ARZ ? rho[CPT - 1] : rho[CPT - 2];
+          xR[xi - pos] = ARZ ? v[CPT - 1] : rho[CPT - 1];
+        }
+      }
+      consumer_sync(NC);                               // exchange visible
+      if (j == 0 && lane0) mbar_arrive(empty0 + 8 * s);  // stage s fully read: release it
+      if (last) mbar_wait(ofree0 + 8 * o, ph_out ^ 1);   // output stage drained by its last store
+
+      if (active) {
+        T rn[CPT], vn[CPT];
+        const T S_right = xS[xi + 1], D_left = xD[xi], r_left = xR[xi];
+        with_lam<LAMK>(e.flags, [&](auto kind) {
+          constexpr int K = decltype(kind)::value;
+          if (ARZ)
+            arz_pass2<T, FAST, K, CPT>(e, a.bc, row_first, row_last, rho, v, y, r, D, S, S_right,
+                                       D_left, r_left, D_left, r_left, rn, vn);
+          else
+            lwr_pass2<T, FAST, K, CPT>(e, a.bc, row_first, row_last, rho, D, S, S_right, D_left,
+                                       D_left, r_left, rn, vn);
+        });
+        if (!last) {
+#pragma unroll
+          for (int k = 0; k < CPT; ++k) { rho[k] = rn[k]; v[k] = vn[k]; }
+        } else {
+          if (want_reward) {
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) { num += rn[k] * vn[k]; den += rn[k]; }
+          }
+          const uint32_t dst = out0 + (uint32_t)o * PIPE_TILE_BYTES + my_off;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            T tr[V], tv[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) { tr[k] = rn[u * V + k]; tv[k] = vn[u * V + k]; }
+            sts16(dst + 16 * u, tr);
+            sts16(dst + v_off + 16 * u, tv);
+          }
+        }
+      }
+    }
+    fence_proxy_async_smem();  // my generic-proxy writes -> visible to the bulk engine
+    __syncwarp();
+    if (lane0) mbar_arrive(ofull0 + 8 * o);          // non-blocking hand-off to the producer
+
+    if (want_reward) {
+      // per-road sum(rho v)/sum(rho) in a fixed order
+      const unsigned full = 0xffffffffu;
+      if (a.tpe <= 32) {
+        for (int off = a.tpe >> 1; off > 0; off >>= 1) {
+          num += __shfl_xor_sync(full, num, off);
+          den += __shfl_xor_sync(full, den, off);
+        }
+        if (active && row_first) a.reward[env] = num / den;
+      } else {
+        for (int off = 16; off > 0; off >>= 1) {
+          num += __shfl_xor_sync(full, num, off);
+          den += __shfl_xor_sync(full, den, off);
+        }
+        if (lane0) { sm.s_num[t >> 5] = num; sm.s_den[t >> 5] = den; }
+        consumer_sync(NC);
+        if (active && row_first) {
+          const int w0 = t >> 5, nw = a.tpe >> 5;
+          T n = sm.s_num[w0], d = sm.s_den[w0];
+          for (int j = 1; j < nw; ++j) { n += sm.s_num[w0 + j]; d += sm.s_den[w0 + j]; }
+          a.reward[env] = n / d;
+        }
+      }
+    }
+    if (++s == PIPE_STAGES) { s = 0; ph_in ^= 1; }
+    if (++o == PIPE_OUT) { o = 0; ph_out ^= 1; }
+  }
+}
+
+}  // namespace mt

@@ -200,6 +200,8 @@ template <typename T> struct PipeArgs {
   int n_tiles;
   int nc;      // consumer threads per CTA (the CTA has nc + 32 threads)
   int l2_ahead;  // tiles prefetched into L2 beyond the shared-memory ring
+  int n_inner;   // model steps per tile visit (step_fused_kernel, mt_fused.cuh)
+  long long action_stride;  // elements between consecutive steps' actions
   BcArgs<T> bc;
   T step;
   UniformC<T> u;  // used by the UNIFORM instantiations

@@ -14,6 +14,7 @@
 #include "mt_math.cuh"
 #include "mt_pipe.cuh"
 #include "mt_ring.cuh"
+#include "mt_fused.cuh"
 #include "mt_seg.cuh"
 #include "mt_direct.cuh"
 #include "mt_nonlocal.cuh"
@@ -240,16 +241,22 @@ int launch_pipe(const PipeArgs<T>& pa, int grid, cudaStream_t stream) {
     CUDA_TRY(cudaFuncSetAttribute(step_pipe_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)sizeof(PipeSmem<T, U>)));
+    CUDA_TRY(cudaFuncSetAttribute(step_fused_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(PipeSmem<T, U>)));
     CUDA_TRY(cudaFuncSetAttribute(step_ring_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)sizeof(RingSmem<T, U>)));
     configured = true;
   }
-  if (pipe_use_ring(sizeof(T) == 4, FAST))
+  if (pa.n_inner == 1 && pipe_use_ring(sizeof(T) == 4, FAST))
     return launch_pdl(step_ring_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>, pa, grid, pa.nc,
                       sizeof(RingSmem<T, U>), stream);
-  return launch_pdl(step_pipe_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>, pa, grid, pa.nc + 32,
-                    sizeof(PipeSmem<T, U>), stream);
+  if (pa.n_inner > 1)
+    return launch_pdl(step_fused_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>, pa, grid,
+                      pa.nc + 32, sizeof(PipeSmem<T, U>), stream);
+  return launch_pdl(step_pipe_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>, pa, grid,
+                    pa.nc + 32, sizeof(PipeSmem<T, U>), stream);
 }
 
 template <typename T, int MODEL, bool FAST, int U>
@@ -467,7 +474,8 @@ int launch_seg_fast(const SegArgs<T>& sa, int grid, bool fast, bool uniform, int
 // whole batch (road 0) and are offset here.
 template <typename T>
 int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs_out_,
-               void* reward_out_, long long env0, long long n_env, cudaStream_t stream) {
+               void* reward_out_, long long env0, long long n_env, cudaStream_t stream,
+               int n_inner = 1, long long action_stride = -1) {
   constexpr int V = Vec<T>::N;
   const mt_params& p = e->params;
   const long long B = n_env;
@@ -494,9 +502,11 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
   const T step = (T)(p.dt / p.dx);
 
   if (g.grid > 0x7fffffffLL) return fail(MT_EINVAL, "batch too large for one launch");
-  if (e->cfg.model == MT_MODEL_NONLOCAL)
+  if (e->cfg.model == MT_MODEL_NONLOCAL) {
+    if (n_inner != 1) return fail(MT_EINVAL, "fused multi-step needs the pipelined kernel");
     return step_nonlocal<T>(e, obs_in, action, obs_out, reward_out, table, flags, B, aligned, bc,
                             step, stream);
+  }
   if (g.vector_ok && g.tiles == 1 && !(p.flags & MT_FLAG_NO_PIPELINE)) {
     // persistent TMA-pipelined kernel: tiles of consecutive roads
     int U = pipe_vectors_per_thread();
@@ -515,6 +525,8 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
     pa.nthr = N / (U * V);
     pa.nc = PIPE_BLOCK / U;
     pa.l2_ahead = pipe_l2_ahead();
+    pa.n_inner = n_inner;
+    pa.action_stride = action_stride >= 0 ? action_stride : e->cfg.n_envs;
     pa.tpe = pa.nthr <= 32 ? next_pow2(pa.nthr) : ((pa.nthr + 31) / 32) * 32;
     pa.epc = pa.nc / pa.tpe;
     if (pa.epc > PIPE_MAX_EPC) pa.epc = PIPE_MAX_EPC;
@@ -539,6 +551,7 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
     return MT_OK;
   }
 
+  if (n_inner != 1) return fail(MT_EINVAL, "fused multi-step needs the pipelined kernel");
   if (g.vector_ok && g.tiles > 1 && !(p.flags & MT_FLAG_NO_PIPELINE) && B <= 0x7fffffffLL) {
     // a road longer than one tile: segments of it flow through the pipeline
     int U = pipe_vectors_per_thread();
@@ -640,11 +653,26 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
   return MT_OK;
 }
 
+// True when n_steps chained steps of this batch can run as ONE launch of the
+// pipelined kernel with the state kept in registers between steps: LWR / ARZ,
+// roads that fit one tile, 16-byte aligned buffers.
+bool can_fuse_steps(const mt_engine* e, const void* obs_in, const void* obs_out) {
+  if (e->cfg.model == MT_MODEL_NONLOCAL || (e->params.flags & MT_FLAG_NO_PIPELINE)) return false;
+  const int V = (int)(16 / e->elt);
+  const bool aligned = (((uintptr_t)obs_in | (uintptr_t)obs_out) & 15u) == 0;
+  const Geometry g = plan(e->cfg.n_envs, (int)e->cfg.n_cells, V, aligned);
+  const char* off = getenv("MT_NO_FUSE");
+  return g.vector_ok && g.tiles == 1 && !(off && off[0] == '1');
+}
+
 int step_range(mt_engine* e, const void* obs_in, const void* action, void* obs_out,
-               void* reward_out, long long env0, long long n_env, cudaStream_t stream) {
+               void* reward_out, long long env0, long long n_env, cudaStream_t stream,
+               int n_inner = 1, long long action_stride = -1) {
   if (e->cfg.dtype == MT_F64)
-    return step_typed<double>(e, obs_in, action, obs_out, reward_out, env0, n_env, stream);
-  return step_typed<float>(e, obs_in, action, obs_out, reward_out, env0, n_env, stream);
+    return step_typed<double>(e, obs_in, action, obs_out, reward_out, env0, n_env, stream, n_inner,
+                              action_stride);
+  return step_typed<float>(e, obs_in, action, obs_out, reward_out, env0, n_env, stream, n_inner,
+                           action_stride);
 }
 
 int step_any(mt_engine* e, const void* obs_in, const void* action, void* obs_out,
@@ -803,6 +831,20 @@ int mt_rollout(mt_engine* e, void* obs_a, void* obs_b, const void* actions, void
   if (n_steps < 0) return fail(MT_EINVAL, "mt_rollout: n_steps must be >= 0");
   CUDA_TRY(cudaSetDevice(e->cfg.device));
   const size_t stride = (size_t)e->cfg.n_envs * e->elt;
+  if (n_steps >= 2 && !rewards && can_fuse_steps(e, obs_a, obs_b)) {
+    // one launch: every tile is read once, stepped n_steps times on chip
+    // (per-step actions are read as they are needed) and written once
+    if (e->params_pending) {
+      if ((cudaStream_t)stream != e->params_stream)
+        CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, e->params_ready, 0));
+      e->params_pending = false;
+    }
+    const int rc = step_range(e, obs_a, actions, obs_b, nullptr, 0, e->cfg.n_envs,
+                              (cudaStream_t)stream, n_steps);
+    if (rc != MT_OK) return rc;
+    if (result_in_b) *result_in_b = 1;
+    return MT_OK;
+  }
   void* cur = obs_a;
   void* nxt = obs_b;
   for (int s = 0; s < n_steps; ++s) {
@@ -849,8 +891,11 @@ int mt_step_host(mt_engine* e, const void* obs_in_host, const void* action_host,
     CUDA_TRY(cudaEventRecord(e->action_ready, e->hs[0]));
     for (int i = 1; i < NS; ++i) CUDA_TRY(cudaStreamWaitEvent(e->hs[i], e->action_ready, 0));
   }
+  // several steps on one upload: fused into one launch per chunk when possible
+  // (the same speed limits apply to every step: action stride 0)
+  const bool fuse = n_steps >= 2 && can_fuse_steps(e, e->d_a, e->d_b);
   const bool odd = (n_steps & 1) != 0;
-  char* result = (char*)(odd ? e->d_b : e->d_a);
+  char* result = (char*)((odd || fuse) ? e->d_b : e->d_a);
   for (long long c = 0; c < n_chunks; ++c) {
     const long long env0 = c * per;
     const long long n_env = (env0 + per <= B) ? per : B - env0;
@@ -861,12 +906,19 @@ int mt_step_host(mt_engine* e, const void* obs_in_host, const void* action_host,
                              cudaMemcpyHostToDevice, s));
     void* cur = e->d_a;
     void* nxt = e->d_b;
-    for (int i = 0; i < n_steps; ++i) {
-      void* rew = (reward_out_host && i == n_steps - 1) ? e->d_reward : nullptr;
-      const int rc = step_range(e, cur, action_host ? e->d_action : nullptr, nxt, rew, env0,
-                                n_env, s);
+    if (fuse) {
+      const int rc = step_range(e, cur, action_host ? e->d_action : nullptr, nxt,
+                                reward_out_host ? e->d_reward : nullptr, env0, n_env, s,
+                                n_steps, 0);
       if (rc != MT_OK) return rc;
-      void* tmp = cur; cur = nxt; nxt = tmp;
+    } else {
+      for (int i = 0; i < n_steps; ++i) {
+        void* rew = (reward_out_host && i == n_steps - 1) ? e->d_reward : nullptr;
+        const int rc = step_range(e, cur, action_host ? e->d_action : nullptr, nxt, rew, env0,
+                                  n_env, s);
+        if (rc != MT_OK) return rc;
+        void* tmp = cur; cur = nxt; nxt = tmp;
+      }
     }
     CUDA_TRY(cudaMemcpyAsync((char*)obs_out_host + off, result + off, bytes,
                              cudaMemcpyDeviceToHost, s));

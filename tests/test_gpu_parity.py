@@ -905,3 +905,64 @@ def test_aggregate_micro_is_bit_equal_to_the_notebook_loop(sorted_input):
     assert (ref_d == 0).any() and (s.cpu().numpy()[ref_d == 0] == 30).all()
     obs = macro_observations(s, d)
     assert obs.shape == (40, 60)
+
+
+# --------------------------------------------------------------------------- #
+# fused multi-step rollouts: n steps in one launch, state kept on chip        #
+# --------------------------------------------------------------------------- #
+
+@pytest.mark.parametrize("kind", ["lwr", "arz"])
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("n,b", [(8, 301), (30, 77), (250, 40), (1000, 37), (1024, 5)])
+@pytest.mark.parametrize("bci", [0, 1, 2, 3])
+def test_fused_rollout_equals_step_by_step(kind, dtype, n, b, bci, monkeypatch):
+    _need_gpu()
+    from mbrl_traffic_b200.engine import Engine
+    if dtype == "float32" and n % 4:
+        pytest.skip("f32 vectors need N % 4 == 0")
+    bc = BCS[kind][bci]
+    steps = 7
+    obs = make_obs(b, n, seed=n + bci, dtype=np.dtype(dtype))
+    tdt = torch.float64 if dtype == "float64" else torch.float32
+    acts = torch.as_tensor(np.random.default_rng(3).uniform(10, 30, (steps, b)),
+                           device="cuda:0").to(tdt)
+    results = []
+    for fuse in ("0", "1"):
+        monkeypatch.setenv("MT_NO_FUSE", "1" if fuse == "0" else "0")
+        eng = Engine(kind, dtype, b, n)
+        eng.set_params(dx=50, dt=0.5, rho_max=1, v_max=30, lam=1,
+                       boundary_conditions=bc, tau=9)
+        for use_actions in (False, True):
+            a = gpu(obs).clone()
+            bb = torch.empty_like(a)
+            res = eng.rollout(a, bb, steps, actions=acts if use_actions else None)
+            results.append(res.clone())
+        eng.close()
+    torch.cuda.synchronize()
+    assert torch.equal(results[0], results[2])     # no actions: stepwise == fused
+    assert torch.equal(results[1], results[3])     # per-step actions
+    if dtype == "float64":
+        ref = obs
+        for _ in range(steps):
+            ref = _oracle_with_extension(kind, ref, bc)
+        assert np.array_equal(results[2].cpu().numpy(), ref)
+
+
+def test_fused_host_run_with_final_reward():
+    _need_gpu()
+    from mbrl_traffic_b200.engine import Engine
+    b, n, steps = 300, 1000, 9
+    obs = make_obs(b, n, seed=81)
+    eng = Engine("arz", "float64", b, n, host_staging=True)
+    eng.set_params(dx=50, dt=0.5, rho_max=1, v_max=30, lam=1,
+                   boundary_conditions="loop", tau=9, stream=0)
+    out = np.empty_like(obs)
+    rew = np.empty(b)
+    act = np.full(b, 22.0)
+    eng.step_host(obs, out, action=act, reward=rew, n_steps=steps)
+    ref = obs
+    for _ in range(steps):
+        ref = o.arz_step(ref, v_max=22.0)
+    assert np.array_equal(out, ref)
+    np.testing.assert_allclose(rew, o.mean_speed_reward(ref), rtol=1e-12)
+    eng.close()
