@@ -210,21 +210,22 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_fused_ker
           xR[xi - pos] = ARZ ? v[CPT - 1] : rho[CPT - 1];
         }
       }
+      T rn[CPT], vn[CPT], Q[CPT], P[CPT];
+      if (active) {  // interior cells need nothing from other threads: finish them first
+        with_lam<LAMK>(e.flags, [&](auto kind) {
+          cell_mid<T, ARZ, FAST, decltype(kind)::value, CPT>(e, rho, y, r, D, S, Q, P, rn, vn);
+        });
+      }
       consumer_sync(NC);                               // exchange visible
       if (j == 0 && lane0) mbar_arrive(empty0 + 8 * s);  // stage s fully read: release it
       if (last) mbar_wait(ofree0 + 8 * o, ph_out ^ 1);   // output stage drained by its last store
 
       if (active) {
-        T rn[CPT], vn[CPT];
         const T S_right = xS[xi + 1], D_left = xD[xi], r_left = xR[xi];
         with_lam<LAMK>(e.flags, [&](auto kind) {
-          constexpr int K = decltype(kind)::value;
-          if (ARZ)
-            arz_pass2<T, FAST, K, CPT>(e, a.bc, row_first, row_last, rho, v, y, r, D, S, S_right,
-                                       D_left, r_left, D_left, r_left, rn, vn);
-          else
-            lwr_pass2<T, FAST, K, CPT>(e, a.bc, row_first, row_last, rho, D, S, S_right, D_left,
-                                       D_left, r_left, rn, vn);
+          cell_edges<T, ARZ, FAST, decltype(kind)::value, CPT>(
+              e, a.bc, row_first, row_last, rho, v, y, r, D, S, Q, P, S_right, D_left, r_left,
+              D_left, r_left, rn, vn);
         });
         if (!last) {
 #pragma unroll

@@ -388,23 +388,28 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
       xD[xi + 1] = D[CPT - 1];
       if (row_last) xS[xi + 1] = S[CPT - 1];  // arz.py:405 / lwr.py:294
     }
+    T num = 0, den = 0;
+    T rn[CPT], vn[CPT];
+    // finish my interior cells -- they need nothing from other threads --
+    // before the barrier: less state lives across it, less work follows it
+    T Q[CPT], P[CPT];  // my fluxes (LWR: Q only)
+    if (active) {
+      with_lam<LAMK>(e.flags, [&](auto kind) {
+        cell_mid<T, ARZ, FAST, decltype(kind)::value, CPT>(e, rho, y, r, D, S, Q, P, rn, vn);
+      });
+    }
     consumer_sync(NC);                               // exchange visible; stage s fully read
     if (lane0) mbar_arrive(empty0 + 8 * s);          // release the input stage
     mbar_wait(ofree0 + 8 * o, ph_out ^ 1);           // output stage drained by its last store
-
-    T num = 0, den = 0;
     if (active) {
-      T rn[CPT], vn[CPT];
       const T S_right = xS[xi + 1], D_left = xD[xi], r_left = ARZ ? xR[xi] : T(0);
       with_lam<LAMK>(e.flags, [&](auto kind) {
-        constexpr int K = decltype(kind)::value;
-        if (ARZ)
-          arz_pass2<T, FAST, K, CPT>(e, a.bc, row_first, row_last, rho, v, y, r, D, S, S_right,
-                                     D_left, r_left, loop_a, loop_b, rn, vn);
-        else
-          lwr_pass2<T, FAST, K, CPT>(e, a.bc, row_first, row_last, rho, D, S, S_right, D_left,
-                                     loop_a, loop_b, rn, vn);
+        cell_edges<T, ARZ, FAST, decltype(kind)::value, CPT>(
+            e, a.bc, row_first, row_last, rho, v, y, r, D, S, Q, P, S_right, D_left, r_left,
+            loop_a, loop_b, rn, vn);
       });
+    }
+    if (active) {
       if (want_reward) {
 #pragma unroll
         for (int k = 0; k < CPT; ++k) { num += rn[k] * vn[k]; den += rn[k]; }

@@ -221,6 +221,12 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) step_seg_kernel(const 
       xD[xi + 1] = D[CPT - 1];
       if (row_last) xS[xi + 1] = S[CPT - 1];
     }
+    T rn[CPT], vn[CPT], Q[CPT], P[CPT];
+    if (active) {  // interior cells need nothing from other threads: finish them first
+      with_lam<LAMK>(e.flags, [&](auto kind) {
+        cell_mid<T, ARZ, FAST, decltype(kind)::value, CPT>(e, rho, y, r, D, S, Q, P, rn, vn);
+      });
+    }
     consumer_sync(NC);
     if (lane0) mbar_arrive(empty0 + 8 * s);
     mbar_wait(ofree0 + 8 * o, ph_out ^ 1);
@@ -228,7 +234,6 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) step_seg_kernel(const 
     T num = 0, den = 0;
     if (active) {
       T S_right = xS[xi + 1], D_left = xD[xi], r_left = xR[xi];
-      T rn[CPT], vn[CPT];
       with_lam<LAMK>(e.flags, [&](auto kind) {
         constexpr int K = decltype(kind)::value;
         if (seg_last && !row_last) {          // supply of the next segment's first cell
@@ -241,12 +246,8 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) step_seg_kernel(const 
           if (ARZ) arz_cell<T, FAST, K>(e, hl_rho, hl_v, yy, r_left, D_left, ss);
           else lwr_cell<T, FAST, K>(e, hl_rho, D_left, ss);
         }
-        if (ARZ)
-          arz_pass2<T, FAST, K, CPT>(e, a.bc, row_first, row_last, rho, v, y, r, D, S, S_right,
-                                     D_left, r_left, loop_a, loop_b, rn, vn);
-        else
-          lwr_pass2<T, FAST, K, CPT>(e, a.bc, row_first, row_last, rho, D, S, S_right, D_left,
-                                     loop_a, loop_b, rn, vn);
+        cell_edges<T, ARZ, FAST, K, CPT>(e, a.bc, row_first, row_last, rho, v, y, r, D, S, Q, P,
+                                         S_right, D_left, r_left, loop_a, loop_b, rn, vn);
       });
       if (want_reward) {
 #pragma unroll
