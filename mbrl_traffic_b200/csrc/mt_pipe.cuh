@@ -164,6 +164,7 @@ __device__ __forceinline__ void sts16(uint32_t addr, const float (&a)[4]) {
 }
 
 // ---- shared-memory layout ---------------------------------------------------
+constexpr int PIPE_QMAX = 4;  // bound of the L2 look-ahead (power of two)
 template <typename T, int U> struct PipeSmem {
   static constexpr int STAGES = PipeCfg<T, U>::STAGES;
   static constexpr int XCH = PipeCfg<T, U>::XCH;
@@ -178,6 +179,8 @@ template <typename T, int U> struct PipeSmem {
   uint64_t empty[STAGES];                   // consumers -> producer: stage read
   uint64_t out_full[PIPE_OUT];              // consumers -> producer: result staged
   uint64_t out_free[PIPE_OUT];              // producer -> consumers: store drained
+  int tile_of[STAGES];                      // dynamic schedule: tile in each stage; -1: no more
+  int drawn[PIPE_QMAX];                     // producer: tiles drawn + L2-prefetched, not yet loaded
 };
 // two CTAs per SM: 2 x (smem + 1 KB reserved) <= 228 KB
 static_assert(sizeof(PipeSmem<double, 2>) <= (228 / PIPE_CTAS - 1) * 1024, "f64 U=2 smem");
@@ -185,7 +188,22 @@ static_assert(sizeof(PipeSmem<float, 2>) <= (228 / PIPE_CTAS - 1) * 1024, "f32 U
 static_assert(PIPE_CTAS >= 3 || sizeof(PipeSmem<double, 1>) <= 113 * 1024, "f64 U=1 smem");
 static_assert(PIPE_CTAS >= 3 || sizeof(PipeSmem<float, 1>) <= 113 * 1024, "f32 U=1 smem");
 
+#ifdef MT_TRACE
+// experimental build only (tools/trace_pipe.py): per-CTA %globaltimer stamps
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+  return v;
+}
+#define MT_STAMP(slot) do { if (a.trace) a.trace[(size_t)blockIdx.x * 8 + (slot)] = gtime(); } while (0)
+#else
+#define MT_STAMP(slot) do {} while (0)
+#endif
+
 template <typename T> struct PipeArgs {
+#ifdef MT_TRACE
+  unsigned long long* trace = nullptr;
+#endif
   const T* in;
   T* out;
   const T* table;
@@ -205,6 +223,19 @@ template <typename T> struct PipeArgs {
   BcArgs<T> bc;
   T step;
   UniformC<T> u;  // used by the UNIFORM instantiations
+  // Dynamic tile schedule of step_pipe_kernel: sched[0] hands out tiles beyond
+  // each CTA's first ring-full, sched[1] counts finished CTAs (the last one
+  // re-arms both).  nullptr: static round-robin schedule.
+  unsigned int* sched = nullptr;
+};
+
+// Which instantiations of step_pipe_kernel draw their tiles from a counter.
+// Measured on B200: the HBM-bound ones gain (LWR f64 83% ->
+// 99% of the measured peak, ARZ f32 fast 89% -> 93%); ARZ f64 is issue-bound,
+// does not gain, and loses to the extra live state, so it keeps the static
+// round-robin schedule.
+template <typename T, int MODEL, bool FAST> struct PipeDynamic {
+  static constexpr bool value = !(MODEL == 1 && sizeof(T) == 8);
 };
 
 // MODEL: 0 = LWR, 1 = ARZ.  LAMK: exponent kind fixed at compile time, or
@@ -215,6 +246,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
   constexpr int V = Vec<T>::N;
   constexpr int CPT = U * V;
   constexpr bool ARZ = (MODEL == 1);
+  constexpr bool DYN = PipeDynamic<T, MODEL, FAST>::value;
   constexpr int PIPE_STAGES = PipeCfg<T, U>::STAGES;
   constexpr int PIPE_XCH = PipeCfg<T, U>::XCH;
   using A = Ar<T, FAST>;
@@ -234,6 +266,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
   const uint32_t full0 = smem_u32(&sm.full[0]), empty0 = smem_u32(&sm.empty[0]);
   const uint32_t ofull0 = smem_u32(&sm.out_full[0]), ofree0 = smem_u32(&sm.out_free[0]);
 
+  if (t == 0) MT_STAMP(0);
   pdl_launch_dependents();
   // pad slots of the exchange arrays stay zero for the kernel's life: they
   // feed the (discarded) left-face flux of each road's first cell
@@ -260,58 +293,155 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
       auto bytes_of = [&](int tile) -> uint32_t {
         return tile == last_tile ? (uint32_t)last_envs * row_bytes : tile_bytes;
       };
-      auto issue_load = [&](int i) {
-        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-        const int s = i % PIPE_STAGES;
-        if (ARZ) {
-          const uint32_t bytes = bytes_of(tile);
-          mbar_expect_tx(full0 + 8 * s, bytes);
-          bulk_load(in0 + (uint32_t)s * PIPE_TILE_BYTES, gin + (size_t)tile * tile_bytes, bytes,
-                    full0 + 8 * s);
-        } else {
-          // LWR ignores the input velocity (lwr.py:197): fetch the density half
-          // of each road only, at its usual place in the stage
-          const int envs = tile == last_tile ? last_envs : a.epc;
-          const uint32_t half = row_bytes >> 1;
-          mbar_expect_tx(full0 + 8 * s, (uint32_t)envs * half);
-          for (int r = 0; r < envs; ++r)
-            bulk_load(in0 + (uint32_t)s * PIPE_TILE_BYTES + (uint32_t)r * row_bytes,
-                      gin + (size_t)tile * tile_bytes + (size_t)r * row_bytes, half,
+      if constexpr (!DYN) {
+        auto issue_load = [&](int i) {
+          const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+          const int s = i % PIPE_STAGES;
+          if (ARZ) {
+            const uint32_t bytes = bytes_of(tile);
+            mbar_expect_tx(full0 + 8 * s, bytes);
+            bulk_load(in0 + (uint32_t)s * PIPE_TILE_BYTES, gin + (size_t)tile * tile_bytes, bytes,
                       full0 + 8 * s);
+          } else {
+            // LWR ignores the input velocity (lwr.py:197): fetch the density half
+            // of each road only, at its usual place in the stage
+            const int envs = tile == last_tile ? last_envs : a.epc;
+            const uint32_t half = row_bytes >> 1;
+            mbar_expect_tx(full0 + 8 * s, (uint32_t)envs * half);
+            for (int r = 0; r < envs; ++r)
+              bulk_load(in0 + (uint32_t)s * PIPE_TILE_BYTES + (uint32_t)r * row_bytes,
+                        gin + (size_t)tile * tile_bytes + (size_t)r * row_bytes, half,
+                        full0 + 8 * s);
+          }
+        };
+        auto prefetch = [&](int i) {
+          const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+          if (ARZ) {
+            bulk_prefetch_l2(gin + (size_t)tile * tile_bytes, bytes_of(tile));
+          } else {
+            const int envs = tile == last_tile ? last_envs : a.epc;
+            for (int r = 0; r < envs; ++r)
+              bulk_prefetch_l2(gin + (size_t)tile * tile_bytes + (size_t)r * row_bytes,
+                               row_bytes >> 1);
+          }
+        };
+        const int pre = n_my < PIPE_STAGES ? n_my : PIPE_STAGES;
+        for (int i = 0; i < pre; ++i) issue_load(i);
+        const int ahead = a.l2_ahead;
+        for (int i = PIPE_STAGES; i < PIPE_STAGES + ahead && i < n_my; ++i) prefetch(i);
+        for (int i = 0; i < n_my; ++i) {
+          const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+          const int s = i % PIPE_STAGES, o = i % PIPE_OUT;
+          if (ahead > 0 && i + PIPE_STAGES + ahead < n_my) prefetch(i + PIPE_STAGES + ahead);
+          if (i + PIPE_STAGES < n_my) {  // refill stage s once the consumers have read tile i
+            mbar_wait_relaxed(empty0 + 8 * s, (uint32_t)((i / PIPE_STAGES) & 1), PRODUCER_NAP_NS);
+            issue_load(i + PIPE_STAGES);
+          }
+          mbar_wait_relaxed(ofull0 + 8 * o, (uint32_t)((i / PIPE_OUT) & 1), PRODUCER_NAP_NS);
+          bulk_store(gout + (size_t)tile * tile_bytes, out0 + (uint32_t)o * PIPE_TILE_BYTES,
+                     bytes_of(tile));
+          bulk_commit();
+          // all but the newest PIPE_OUT-1 stores have finished reading shared memory
+          bulk_wait_read<PIPE_OUT - 1>();
+          if (i >= PIPE_OUT - 1) mbar_arrive(ofree0 + 8 * ((i - (PIPE_OUT - 1)) % PIPE_OUT));
         }
-      };
-      auto prefetch = [&](int i) {
-        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-        if (ARZ) {
-          bulk_prefetch_l2(gin + (size_t)tile * tile_bytes, bytes_of(tile));
-        } else {
-          const int envs = tile == last_tile ? last_envs : a.epc;
-          for (int r = 0; r < envs; ++r)
-            bulk_prefetch_l2(gin + (size_t)tile * tile_bytes + (size_t)r * row_bytes,
-                             row_bytes >> 1);
+      } else {
+        // Tile schedule.  The first ring-full of every CTA is static (tile =
+        // block + g * grid) so nothing waits on an atomic at start-up; after
+        // that the CTAs draw tiles from one counter, which evens out their
+        // finishing times (SMs do not progress at the same rate, and the next
+        // step cannot start before the slowest CTA is done).
+        int g = 0;  // tiles drawn so far
+        auto grab = [&]() -> int {
+          int tl;
+          if (a.sched == nullptr || g < PIPE_STAGES)
+            tl = (int)blockIdx.x + g * (int)gridDim.x;
+          else
+            tl = (int)atomicAdd(a.sched, 1u) + PIPE_STAGES * (int)gridDim.x;
+          ++g;
+          return tl < a.n_tiles ? tl : -1;
+        };
+        // fill stage s with `tile`, or mark it as the end of this CTA's work
+        auto issue_load = [&](int s, int tile) {
+          sm.tile_of[s] = tile;
+          if (tile < 0) {
+            mbar_arrive(full0 + 8 * s);
+            return;
+          }
+          if (ARZ) {
+            const uint32_t bytes = bytes_of(tile);
+            mbar_expect_tx(full0 + 8 * s, bytes);
+            bulk_load(in0 + (uint32_t)s * PIPE_TILE_BYTES, gin + (size_t)tile * tile_bytes, bytes,
+                      full0 + 8 * s);
+          } else {
+            // LWR ignores the input velocity (lwr.py:197): fetch the density half
+            // of each road only, at its usual place in the stage
+            const int envs = tile == last_tile ? last_envs : a.epc;
+            const uint32_t half = row_bytes >> 1;
+            mbar_expect_tx(full0 + 8 * s, (uint32_t)envs * half);
+            for (int r = 0; r < envs; ++r)
+              bulk_load(in0 + (uint32_t)s * PIPE_TILE_BYTES + (uint32_t)r * row_bytes,
+                        gin + (size_t)tile * tile_bytes + (size_t)r * row_bytes, half,
+                        full0 + 8 * s);
+          }
+        };
+        auto prefetch = [&](int tile) {
+          if (tile < 0) return;
+          if (ARZ) {
+            bulk_prefetch_l2(gin + (size_t)tile * tile_bytes, bytes_of(tile));
+          } else {
+            const int envs = tile == last_tile ? last_envs : a.epc;
+            for (int r = 0; r < envs; ++r)
+              bulk_prefetch_l2(gin + (size_t)tile * tile_bytes + (size_t)r * row_bytes,
+                               row_bytes >> 1);
+          }
+        };
+        MT_STAMP(1);
+        for (int s = 0; s < PIPE_STAGES; ++s) issue_load(s, grab());
+        // tiles drawn and prefetched into L2 but not yet loaded: a ring in
+        // shared memory (this thread only), oldest at index i % PIPE_QMAX
+        const int ahead = a.l2_ahead < PIPE_QMAX ? a.l2_ahead : PIPE_QMAX;
+        for (int k = 0; k < ahead; ++k) {
+          const int drawn = grab();
+          prefetch(drawn);
+          sm.drawn[k] = drawn;
         }
-      };
-      const int pre = n_my < PIPE_STAGES ? n_my : PIPE_STAGES;
-      for (int i = 0; i < pre; ++i) issue_load(i);
-      const int ahead = a.l2_ahead;
-      for (int i = PIPE_STAGES; i < PIPE_STAGES + ahead && i < n_my; ++i) prefetch(i);
-      for (int i = 0; i < n_my; ++i) {
-        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-        const int s = i % PIPE_STAGES, o = i % PIPE_OUT;
-        if (ahead > 0 && i + PIPE_STAGES + ahead < n_my) prefetch(i + PIPE_STAGES + ahead);
-        if (i + PIPE_STAGES < n_my) {  // refill stage s once the consumers have read tile i
+        for (int i = 0;; ++i) {
+          const int s = i % PIPE_STAGES, o = i % PIPE_OUT;
+          const int tile = sm.tile_of[s];
+          if (tile < 0) break;
+          const int next = ahead > 0 ? sm.drawn[i & (PIPE_QMAX - 1)] : grab();
+          // refill stage s once the consumers have read tile i
           mbar_wait_relaxed(empty0 + 8 * s, (uint32_t)((i / PIPE_STAGES) & 1), PRODUCER_NAP_NS);
-          issue_load(i + PIPE_STAGES);
+          issue_load(s, next);
+          if (next < 0) MT_STAMP(3);
+          mbar_wait_relaxed(ofull0 + 8 * o, (uint32_t)((i / PIPE_OUT) & 1), PRODUCER_NAP_NS);
+          bulk_store(gout + (size_t)tile * tile_bytes, out0 + (uint32_t)o * PIPE_TILE_BYTES,
+                     bytes_of(tile));
+          bulk_commit();
+          // all but the newest PIPE_OUT-1 stores have finished reading shared memory
+          bulk_wait_read<PIPE_OUT - 1>();
+          if (i >= PIPE_OUT - 1) mbar_arrive(ofree0 + 8 * ((i - (PIPE_OUT - 1)) % PIPE_OUT));
+          if (ahead > 0) {
+            // draw one more tile last: the atomic's round trip then overlaps the
+            // wait for the consumers instead of delaying the load and the store
+            const int drawn = grab();
+            prefetch(drawn);
+            sm.drawn[(i + ahead) & (PIPE_QMAX - 1)] = drawn;
+          }
         }
-        mbar_wait_relaxed(ofull0 + 8 * o, (uint32_t)((i / PIPE_OUT) & 1), PRODUCER_NAP_NS);
-        bulk_store(gout + (size_t)tile * tile_bytes, out0 + (uint32_t)o * PIPE_TILE_BYTES,
-                   bytes_of(tile));
-        bulk_commit();
-        // all but the newest PIPE_OUT-1 stores have finished reading shared memory
-        bulk_wait_read<PIPE_OUT - 1>();
-        if (i >= PIPE_OUT - 1) mbar_arrive(ofree0 + 8 * ((i - (PIPE_OUT - 1)) % PIPE_OUT));
+        if (a.sched != nullptr) {
+          // the last CTA to finish drawing re-arms the schedule for the next launch
+          __threadfence();
+          if (atomicAdd(a.sched + 1, 1u) == gridDim.x - 1) {
+            a.sched[0] = 0u;
+            a.sched[1] = 0u;
+            __threadfence();
+          }
+        }
       }
       bulk_wait_read<0>();  // shared memory must outlive the last bulk store
+      MT_STAMP(6);
     }
     return;
   }
@@ -338,22 +468,31 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
 
   int s = 0, o = 0;
   uint32_t ph_in = 0, ph_out = 0;
-  for (int i = 0; i < n_my; ++i) {
-    const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+  for (int i = 0; DYN || i < n_my; ++i) {
+    int tile;
+    if constexpr (DYN) {
+      // the producer names the tile of each stage; -1 ends this CTA's work
+      mbar_wait(full0 + 8 * s, ph_in);
+      tile = sm.tile_of[s];
+      if (tile < 0) break;
+    } else {
+      tile = (int)blockIdx.x + i * (int)gridDim.x;
+    }
     const int envs_here = tile == last_tile ? last_envs : a.epc;
     const int env = tile * a.epc + el;
     const bool active = owns_cells && (el < envs_here);
 
     if (active && (!UNIFORM || a.action != nullptr)) {
-      // per-road constants (and/or this step's speed limit): issued before the
-      // wait so the loads overlap it
+      // per-road constants (and/or this step's speed limit); with the static
+      // schedule they are issued before the wait so that the loads overlap it
       if (UNIFORM) load_uniform(e, a.u, env, a.action, a.step);
       else load_env(e, a.table, a.flags, env, a.action, a.step);
       if (ARZ) e.qc = A::mul(e.rho_crit, A::mul(e.v_max, e.g_crit));
     }
 
-    mbar_wait(full0 + 8 * s, ph_in);
+    if constexpr (!DYN) mbar_wait(full0 + 8 * s, ph_in);
 
+    if (t == 0) { if (i == 0) MT_STAMP(2); MT_STAMP(4); }
     T rho[CPT], v[CPT], y[CPT], r[CPT], D[CPT], S[CPT];
     T loop_a = 0, loop_b = 0;  // old boundary-source cells for the LOOP rule
     T* const xS = sm.xS[i & 1];
@@ -427,6 +566,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
     fence_proxy_async_smem();  // my generic-proxy writes -> visible to the bulk engine
     __syncwarp();
     if (lane0) mbar_arrive(ofull0 + 8 * o);          // non-blocking hand-off to the producer
+    if (t == 0) MT_STAMP(5);
 
     if (want_reward) {
       // per-road sum(rho v)/sum(rho) in a fixed order

@@ -30,6 +30,10 @@
 namespace {
 
 using namespace mt;
+#ifdef MT_TRACE
+unsigned long long* g_trace = nullptr;
+unsigned g_trace_seq = 0;
+#endif
 
 // ---------------------------------------------------------------------------
 // error plumbing
@@ -139,6 +143,9 @@ struct mt_engine {
   void* table = nullptr;  // [B, TBL_STRIDE]
   int* flags = nullptr;   // [B]
   void* partial = nullptr;
+  // tile-schedule counters of the pipelined kernel: one {next, done} pair per
+  // stream the engine launches on (slot 0: the caller's stream; 1..: hs[])
+  unsigned int* sched = nullptr;
   int max_tiles = 1;
   int sm_count = 148;
   bool have_params = false;
@@ -315,6 +322,21 @@ void make_uniform(UniformC<T>& u, int& lamk, int model, const mt_params& p) {
   u.inv_c = T(1) / c;
   u.flags = lamk | (host_is_pow2((double)rho_max) ? FLAG_RHO_MAX_POW2 : 0) |
             (host_is_pow2((double)c) ? FLAG_C_POW2 : 0);
+}
+
+// Tiles per CTA from which the pipelined kernel draws its tiles from a counter
+// instead of round-robin.  A CTA draws PIPE_STAGES + l2_ahead tiles ahead of
+// the one it computes, so with few tiles per CTA everything is drawn before
+// the CTAs have drifted apart and only the counter's cost remains (measured:
+// DESIGN.md 4.1).  MT_SCHED=static disables it, MT_SCHED=<n> sets the bound.
+int pipe_dynamic_min_tiles() {
+  static int v = -1;
+  if (v < 0) {
+    const char* s = getenv("MT_SCHED");
+    if (s && strcmp(s, "static") == 0) v = 0x7fffffff;
+    else v = (s && atoi(s) > 0) ? atoi(s) : 16;
+  }
+  return v;
 }
 
 int pipe_l2_ahead() {
@@ -536,8 +558,17 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
     pa.bc = bc;
     pa.step = step;
     pa.u = uniform_of<T>(e);
+#ifdef MT_TRACE
+    pa.trace = g_trace ? g_trace + (size_t)((g_trace_seq++) % 8) * 8 * 1024 : nullptr;
+#endif
     const long long slots = (long long)PIPE_CTAS * e->sm_count;
     const int grid = (int)(n_tiles < slots ? n_tiles : slots);
+    if (n_tiles >= (long long)pipe_dynamic_min_tiles() * grid) {
+      int slot = 0;
+      for (int j = 0; j < mt_engine::HOST_STREAMS; ++j)
+        if (e->hs[j] != nullptr && stream == e->hs[j]) slot = j + 1;
+      pa.sched = e->sched + 2 * slot;
+    }
     int rc;
     if (e->cfg.model == MT_MODEL_ARZ)
       rc = U == 2 ? launch_pipe_model<T, 1, 2>(pa, grid, fast, e->uniform, e->lamk, stream)
@@ -727,6 +758,9 @@ int mt_create(const mt_config* cfg, mt_engine** out) {
   cudaError_t err = cudaMalloc(&e->table, B * TBL_STRIDE * e->elt);
   if (err == cudaSuccess) err = cudaMalloc((void**)&e->flags, B * sizeof(int));
   if (err == cudaSuccess && g.tiles > 1) err = cudaMalloc(&e->partial, B * g.tiles * 2 * e->elt);
+  const size_t sched_bytes = 2 * (1 + mt_engine::HOST_STREAMS) * sizeof(unsigned int);
+  if (err == cudaSuccess) err = cudaMalloc((void**)&e->sched, sched_bytes);
+  if (err == cudaSuccess) err = cudaMemset(e->sched, 0, sched_bytes);
   if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
   if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->params_ready, cudaEventDisableTiming);
   if (err == cudaSuccess && cfg->host_staging) {
@@ -754,6 +788,7 @@ void mt_destroy(mt_engine* e) {
   cudaFree(e->table);
   cudaFree(e->flags);
   cudaFree(e->partial);
+  cudaFree(e->sched);
   cudaFree(e->d_a);
   cudaFree(e->d_b);
   cudaFree(e->d_action);
@@ -989,6 +1024,11 @@ int mt_aggregate(const void* time, const void* position, const void* speed, int6
   if (unsorted) return fail(MT_EINVAL, "mt_aggregate: records must be grouped by non-decreasing time row");
   return MT_OK;
 }
+
+#ifdef MT_TRACE
+// experimental build only: 8 launches x 1024 CTAs x 8 stamps, round-robin by launch
+int mt_debug_trace(void* dev_buf) { g_trace = (unsigned long long*)dev_buf; g_trace_seq = 0; return MT_OK; }
+#endif
 
 int mt_launch_count(const mt_engine* e, int64_t* out) {
   if (!e || !out) return fail(MT_EINVAL, "mt_launch_count: NULL argument");
