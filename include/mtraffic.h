@@ -82,8 +82,9 @@ typedef enum mt_bc {
 
 enum {
   /* mt_params.flags */
-  MT_FLAG_FAST_MATH = 1,  /* allow FMA contraction and approximate division
-                             (not bit-comparable; f32 throughput mode)     */
+  MT_FLAG_FAST_MATH = 1,  /* allow FMA contraction, approximate division and
+                             x**lam as exp(lam log x) for a general lam
+                             (not bit-comparable; throughput mode)         */
   MT_FLAG_NO_PIPELINE = 2 /* use the direct (one CTA per road tile) kernel
                              instead of the persistent TMA-pipelined one;
                              same results, for A/B measurements and tests  */

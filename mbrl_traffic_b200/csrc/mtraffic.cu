@@ -63,14 +63,10 @@ template <typename T> struct ParamArgs {
   int* flags;
   long long B;
   int model;
+  int pow_fast;  // MT_FLAG_FAST_MATH
   double rho_max, v_max, tau, lam, rho_crit, dt;
   const T *rho_max_env, *v_max_env, *tau_env, *lam_env, *rho_crit_env;
 };
-
-template <typename T> __device__ __forceinline__ bool is_pow2(T x) {
-  int ex;
-  return x > T(0) && frexp((double)x, &ex) == 0.5;
-}
 
 template <typename T>
 __global__ void set_params_kernel(const ParamArgs<T> p) {
@@ -94,15 +90,14 @@ __global__ void set_params_kernel(const ParamArgs<T> p) {
   else if (lam == T(2)) kind = LAM_TWO;
   else if (lam == T(0.5)) kind = LAM_HALF;
   int fl = kind;
-  if (is_pow2(rho_max)) fl |= FLAG_RHO_MAX_POW2;
-  if (is_pow2(c)) fl |= FLAG_C_POW2;
+  if (p.pow_fast) fl |= FLAG_POW_FAST;
   // (1 - rho_crit/rho_max) ** lam  for q_max (arz.py:396)
   const T base = A::sub(T(1), A::div(rho_crit, rho_max));
   T g;
   if (kind == LAM_ONE) g = base;
   else if (kind == LAM_TWO) g = A::mul(base, base);
   else if (kind == LAM_HALF) g = mt_sqrt(base);
-  else g = mt_pow(base, lam);
+  else g = p.pow_fast ? mt_pow_fast(base, lam) : mt_pow(base, lam);
   T* row = p.table + env * TBL_STRIDE;
   row[TBL_RHO_MAX] = rho_max;
   row[TBL_INV_RHO_MAX] = A::div(T(1), rho_max);
@@ -292,11 +287,6 @@ template <typename T> const UniformC<T>& uniform_of(const mt_engine* e);
 template <> const UniformC<double>& uniform_of<double>(const mt_engine* e) { return e->u64; }
 template <> const UniformC<float>& uniform_of<float>(const mt_engine* e) { return e->u32; }
 
-bool host_is_pow2(double x) {
-  int ex;
-  return x > 0 && frexp(x, &ex) == 0.5;
-}
-
 // Host restatement of set_params_kernel for an all-scalar parameter set with
 // lam in {1, 2, 0.5}: +, -, *, / and sqrt are IEEE on both sides, so these
 // constants equal the device table bit for bit.
@@ -320,8 +310,7 @@ void make_uniform(UniformC<T>& u, int& lamk, int model, const mt_params& p) {
   u.g_crit = g;
   u.c = c;
   u.inv_c = T(1) / c;
-  u.flags = lamk | (host_is_pow2((double)rho_max) ? FLAG_RHO_MAX_POW2 : 0) |
-            (host_is_pow2((double)c) ? FLAG_C_POW2 : 0);
+  u.flags = lamk;
 }
 
 // Tiles per CTA from which the pipelined kernel draws its tiles from a counter
@@ -817,14 +806,16 @@ int mt_set_params(mt_engine* e, const mt_params* p, void* stream) {
   const unsigned grid = (unsigned)((B + block - 1) / block);
   cudaStream_t s = (cudaStream_t)stream;
   if (e->cfg.dtype == MT_F64) {
-    ParamArgs<double> a{(double*)e->table, e->flags, B, e->cfg.model, p->rho_max, p->v_max,
+    ParamArgs<double> a{(double*)e->table, e->flags, B, e->cfg.model,
+                        (p->flags & MT_FLAG_FAST_MATH) ? 1 : 0, p->rho_max, p->v_max,
                         p->tau, p->lam, p->rho_crit, p->dt,
                         (const double*)p->rho_max_env, (const double*)p->v_max_env,
                         (const double*)p->tau_env, (const double*)p->lam_env,
                         (const double*)p->rho_crit_env};
     set_params_kernel<double><<<grid, block, 0, s>>>(a);
   } else {
-    ParamArgs<float> a{(float*)e->table, e->flags, B, e->cfg.model, p->rho_max, p->v_max,
+    ParamArgs<float> a{(float*)e->table, e->flags, B, e->cfg.model,
+                       (p->flags & MT_FLAG_FAST_MATH) ? 1 : 0, p->rho_max, p->v_max,
                        p->tau, p->lam, p->rho_crit, p->dt,
                        (const float*)p->rho_max_env, (const float*)p->v_max_env,
                        (const float*)p->tau_env, (const float*)p->lam_env,

@@ -274,6 +274,21 @@ def test_general_lambda_is_close():
         m.close()
 
 
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-11), (np.float32, 2e-5)])
+def test_general_lambda_fast_math(dtype, tol):
+    """MT_FLAG_FAST_MATH evaluates x**lam as exp(lam log x): close to the
+    oracle (about |lam ln x| * eps per evaluation), not within pow()'s ulp."""
+    _need_gpu()
+    obs = make_obs(64, 1000, lam=2.3, seed=5, dtype=dtype)
+    for kind in ("lwr", "arz"):
+        m = make_model(kind, lam=2.3, fast_math=True)
+        out = m.get_next_obs(gpu(obs), None).cpu().numpy()
+        ref = oracle_step(kind, obs.astype(np.float64), lam=2.3)
+        err = np.abs(out - ref) / np.maximum(np.abs(ref), 1.0)
+        assert err.max() <= tol, err.max()
+        m.close()
+
+
 def test_arz_rho_crit_is_frozen_at_construction():
     _need_gpu()
     obs = make_obs(4, 64, rho_max=0.4, seed=3)

@@ -37,6 +37,9 @@ def main():
     ap.add_argument("--per-env", action="store_true",
                     help="pass the parameters as per-road device arrays")
     ap.add_argument("--rho-max", type=float, default=1.0)
+    ap.add_argument("--lam", type=float, default=1.0)
+    ap.add_argument("--population", action="store_true",
+                    help="one random parameter vector per road (an optimizer's population)")
     args = ap.parse_args()
 
     tdt = torch.float64 if args.dtype == "float64" else torch.float32
@@ -51,9 +54,17 @@ def main():
         if not args.per_env:
             return x
         return torch.full((b,), float(x), dtype=tdt, device="cuda")
-    eng.set_params(dx=50, dt=0.5, rho_max=par(args.rho_max), v_max=par(30), lam=par(1),
-                   boundary_conditions="loop", tau=par(9), fast_math=args.fast,
-                   no_pipeline=args.direct, gamma=gamma)
+    if args.population:
+        g = torch.Generator(device="cuda").manual_seed(1)
+        def rnd(lo, hi):
+            return lo + (hi - lo) * torch.rand(b, generator=g, dtype=tdt, device="cuda")
+        eng.set_params(dx=50, dt=0.5, rho_max=rnd(0.9, 1.5) * args.rho_max, v_max=rnd(20, 40),
+                       lam=rnd(0.5, 3.0), boundary_conditions="loop", tau=rnd(5, 25),
+                       fast_math=args.fast, no_pipeline=args.direct, gamma=gamma)
+    else:
+        eng.set_params(dx=50, dt=0.5, rho_max=par(args.rho_max), v_max=par(30),
+                       lam=par(args.lam), boundary_conditions="loop", tau=par(9),
+                       fast_math=args.fast, no_pipeline=args.direct, gamma=gamma)
     rng = np.random.default_rng(0)
     rho = args.rho_max * rng.uniform(0.05, 0.9, (b, n))
     v = 30 * (1 - rho / args.rho_max) + rng.normal(0, 1, (b, n))
