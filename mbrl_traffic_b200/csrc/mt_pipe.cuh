@@ -34,14 +34,22 @@ namespace mt {
 #endif
 constexpr int PIPE_CTAS = MT_PIPE_CTAS;
 constexpr int PIPE_BLOCK = 512;                   // consumer threads at U = 1
+#ifdef MT_PIPE_OUT_STAGES
+constexpr int PIPE_OUT = MT_PIPE_OUT_STAGES;      // (experiments)
+#else
 constexpr int PIPE_OUT = (PIPE_CTAS >= 3) ? 1 : 2;
+#endif
 constexpr int PIPE_TILE_BYTES = PIPE_BLOCK * 32;  // 16 KB
 constexpr int PIPE_MAX_EPC = 64;                  // roads per tile (cap)
 // input stages: as many as fit next to the exchange arrays with two CTAs per SM
 template <typename T, int U> struct PipeCfg {
   static constexpr int NC = PIPE_BLOCK / U;                     // consumer threads
   static constexpr int XCH = NC + PIPE_MAX_EPC + 8;             // one pad slot per road
+#ifdef MT_PIPE_IN_STAGES
+  static constexpr int STAGES = MT_PIPE_IN_STAGES;              // (experiments)
+#else
   static constexpr int STAGES = (PIPE_CTAS >= 3) ? 2 : (sizeof(T) == 8 && U == 1) ? 3 : 4;
+#endif
 };
 
 // ---- PTX wrappers -----------------------------------------------------------
@@ -267,6 +275,13 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
   const uint32_t ofull0 = smem_u32(&sm.out_full[0]), ofree0 = smem_u32(&sm.out_free[0]);
 
   if (t == 0) MT_STAMP(0);
+#ifdef MT_TRACE
+  if (t == 0 && a.trace) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    a.trace[(size_t)blockIdx.x * 8 + 7] = smid;
+  }
+#endif
   pdl_launch_dependents();
   // pad slots of the exchange arrays stay zero for the kernel's life: they
   // feed the (discarded) left-face flux of each road's first cell

@@ -332,7 +332,7 @@ int pipe_l2_ahead() {
   static int v = -1;
   if (v < 0) {
     const char* s = getenv("MT_PIPE_L2_AHEAD");
-    v = s ? atoi(s) : 2;  // measured best on B200
+    v = s ? atoi(s) : 0;  // measured best on B200
     if (v < 0) v = 0;
     if (v > 64) v = 64;
   }

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--cells", type=int, default=1000)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--chained", action="store_true")
+    ap.add_argument("--per-cta", action="store_true")
     args = ap.parse_args()
     lib = _lib.load()
     dev = torch.device("cuda:0")
@@ -79,6 +80,18 @@ def main():
         rows.append(row)
     for r in rows[2:]:
         print(json.dumps(r))
+    if args.per_cta:
+        t = tr[order[-2]]
+        live = t[:, 0] > 0
+        t = t[live].astype(np.int64)
+        t0 = t[:, 0].min()
+        fin = t[:, 6] - t0
+        smid = t[:, 7]
+        idx = np.nonzero(live)[0]
+        by = np.argsort(fin)
+        print("finish order (block, smid, entry, finish ns):")
+        for j in by:
+            print(int(idx[j]), int(smid[j]), int(t[j, 0] - t0), int(fin[j]))
 
 
 if __name__ == "__main__":
