@@ -99,6 +99,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // its spinning does not take issue slots from the consumer warps that share
 // its scheduler.
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, unsigned ns) {
+#ifndef MT_PRODUCER_POLLS
+  // try_wait with a suspend-time hint compiles to NANOSLEEP.SYNCS: the thread
+  // sleeps until the barrier flips (or the hint expires) and issues nothing
+  // meanwhile.  A __nanosleep() poll loop returned within ~15 ns per poll on
+  // B200 and cost 15% of all issued warp instructions (profiles/, round 1).
+  (void)ns;
+  mbar_wait(bar, parity);
+  return;
+#endif
   for (;;) {
     uint32_t done;
     asm volatile(
