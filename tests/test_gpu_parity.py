@@ -191,6 +191,40 @@ def test_config2_shape_one_step_bit_exact():
     m.close()
 
 
+@pytest.mark.parametrize("b,n", [(4800, 1000), (18947, 200)])
+@pytest.mark.parametrize("bci", [0, 2])
+def test_dynamic_tile_schedule_bit_exact(b, n, bci):
+    """Batches with >= 16 tiles per CTA draw their tiles from a counter (LWR,
+    and ARZ in f32 fast mode): same results as the oracle, also with a ragged
+    last tile (18947 roads, 4 roads per tile) and over repeated launches (the
+    last CTA of a launch re-arms the counter)."""
+    _need_gpu()
+    bc = BCS["lwr"][bci]
+    obs = make_obs(b, n, seed=b % 97)
+    m = make_model("lwr", boundary_conditions=bc)
+    x = gpu(obs)
+    ref = oracle_step("lwr", obs, boundary_conditions=bc)
+    for _ in range(3):
+        out = m.get_next_obs(x, None)
+        assert np.array_equal(out.cpu().numpy(), ref)
+    # chained steps keep matching (the counter is back at zero every time)
+    out2 = m.get_next_obs(out, None).cpu().numpy()
+    assert np.array_equal(out2, oracle_step("lwr", ref, boundary_conditions=bc))
+    m.close()
+
+
+def test_dynamic_tile_schedule_f32_fast():
+    _need_gpu()
+    obs32 = make_obs(4800, 1000, seed=21, dtype=np.float32)
+    for kind in ("lwr", "arz"):
+        m = make_model(kind, fast_math=True)
+        out = m.get_next_obs(gpu(obs32), None).cpu().numpy()
+        ref = oracle_step(kind, obs32.astype(np.float64))
+        err = np.abs(out - ref) / np.maximum(np.abs(ref), 1.0)
+        assert err.max() <= 2e-6, err.max()
+        m.close()
+
+
 @pytest.mark.parametrize("kind", ["lwr", "arz"])
 def test_per_env_parameters(kind):
     _need_gpu()
