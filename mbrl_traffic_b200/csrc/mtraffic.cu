@@ -89,8 +89,8 @@ __global__ void set_params_kernel(const ParamArgs<T> p) {
   if (lam == T(1)) kind = LAM_ONE;
   else if (lam == T(2)) kind = LAM_TWO;
   else if (lam == T(0.5)) kind = LAM_HALF;
+  if (kind == LAM_GENERAL && p.pow_fast) kind = LAM_GENERAL_FAST;
   int fl = kind;
-  if (p.pow_fast) fl |= FLAG_POW_FAST;
   // (1 - rho_crit/rho_max) ** lam  for q_max (arz.py:396)
   const T base = A::sub(T(1), A::div(rho_crit, rho_max));
   T g;
