@@ -207,16 +207,18 @@ bool pipe_use_pdl() {
 }
 
 // Which persistent kernel: the producer-warp one (mt_pipe.cuh) measured faster
-// in f64 and f32 FAST, the producer-less ring (mt_ring.cuh) in f32 EXACT
-// (B200, 16384x1000: 87/88 % vs 80/82 % and 71 % vs 81 % of HBM peak).
+// in f64 and f32 FAST, the producer-less ring (mt_ring.cuh) in f32 EXACT --
+// except LWR batches large enough for the dynamic tile schedule, which only
+// the producer-warp kernel has (B200, 16384x1000 f32 EXACT: ARZ 82 % ring vs
+// 74 % pipe, LWR 79 % ring vs 91 % pipe of HBM peak).
 // MT_KERNEL=pipe|ring overrides for A/B runs.
-bool pipe_use_ring(bool is_f32, bool fast) {
+bool pipe_use_ring(bool is_f32, bool fast, bool arz, bool dynamic) {
   static int v = -1;
   if (v < 0) {
     const char* s = getenv("MT_KERNEL");
     v = !s ? 2 : (s[0] == 'r') ? 1 : 0;
   }
-  if (v == 2) return is_f32 && !fast;
+  if (v == 2) return is_f32 && !fast && (arz || !dynamic);
   return v != 0;
 }
 
@@ -251,7 +253,7 @@ int launch_pipe(const PipeArgs<T>& pa, int grid, cudaStream_t stream) {
                                   (int)sizeof(RingSmem<T, U>)));
     configured = true;
   }
-  if (pa.n_inner == 1 && pipe_use_ring(sizeof(T) == 4, FAST))
+  if (pa.n_inner == 1 && pipe_use_ring(sizeof(T) == 4, FAST, MODEL == 1, pa.sched != nullptr))
     return launch_pdl(step_ring_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>, pa, grid, pa.nc,
                       sizeof(RingSmem<T, U>), stream);
   if (pa.n_inner > 1)
