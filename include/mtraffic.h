@@ -134,7 +134,11 @@ int mt_set_params(mt_engine *e, const mt_params *p, void *stream);
  * DEVICE [B] speed limits overriding v_max for this step, or NULL (the
  * reference discards the action, lwr.py:194, arz.py:207).  reward_out: DEVICE
  * [B] density-weighted mean speed of the new state, or NULL.  Asynchronous;
- * no allocation; no host synchronisation. */
+ * no allocation; no host synchronisation.
+ * Launches of ONE engine must be ordered with respect to each other (same
+ * stream, or events between streams): the engine owns device-side scheduling
+ * state (the tile counter of large batches).  Use one engine per stream for
+ * concurrent batches. */
 int mt_step(mt_engine *e, const void *obs_in, const void *action,
             void *obs_out, void *reward_out, void *stream);
 
@@ -170,6 +174,34 @@ int mt_aggregate(const void *time, const void *position, const void *speed,
                  int32_t n_sections, double empty_speed, void *scratch_idx,
                  void *speed_out, void *density_out, int32_t device,
                  void *stream);
+
+/* ---- ghost-cell exchange of a domain-decomposed road over peer memory ----
+ * (one road split over the GPUs of a node; the
+ * reference steps a road as one NumPy vector, arz.py:205-221, and has no
+ * multi-device path).  Each rank owns a mailbox in its own device memory,
+ * mapped into its neighbours through CUDA IPC; mt_halo_push stores this rank's
+ * first / last `halo` own cells into the neighbours' mailboxes and publishes
+ * the exchange number, mt_halo_pull waits for both neighbours' numbers and
+ * fills this rank's ghost cells.  local: DEVICE [2 * n_local] block
+ * [rho | v] with `halo` ghost cells on every internal edge.  Both calls are
+ * asynchronous on `stream`; every rank must issue the same sequence of
+ * push / pull pairs. */
+typedef struct mt_halo mt_halo;
+enum { MT_IPC_HANDLE_BYTES = 64 };
+
+int mt_halo_create(int32_t device, int32_t dtype, int32_t halo, mt_halo **out);
+void mt_halo_destroy(mt_halo *h);
+/* The IPC handle of this rank's mailbox, to be sent to the neighbours. */
+int mt_halo_handle(const mt_halo *h, unsigned char handle_out[MT_IPC_HANDLE_BYTES]);
+/* Map the neighbours' mailboxes (NULL: no neighbour on that side). */
+int mt_halo_connect(mt_halo *h, const unsigned char *left_handle,
+                    const unsigned char *right_handle);
+/* Same-process variant (tests, several ranks emulated by one process). */
+int mt_halo_connect_local(mt_halo *h, mt_halo *left, mt_halo *right);
+int mt_halo_push(mt_halo *h, void *local, int64_t n_local, void *stream);
+int mt_halo_pull(mt_halo *h, void *local, int64_t n_local, void *stream);
+/* Synchronises the device; *timed_out = 1 if a pull gave up waiting. */
+int mt_halo_status(mt_halo *h, int32_t *timed_out);
 
 /* Number of kernels this engine has launched so far. */
 int mt_launch_count(const mt_engine *e, int64_t *out);

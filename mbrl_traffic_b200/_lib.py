@@ -23,6 +23,8 @@ EXPORTS = (
     "mt_version", "mt_last_error", "mt_create", "mt_destroy", "mt_set_params",
     "mt_step", "mt_rollout", "mt_step_host", "mt_density_sqerr",
     "mt_launch_count", "mt_alloc_pinned", "mt_free_pinned", "mt_aggregate",
+    "mt_halo_create", "mt_halo_destroy", "mt_halo_handle", "mt_halo_connect",
+    "mt_halo_connect_local", "mt_halo_push", "mt_halo_pull", "mt_halo_status",
 )
 
 
@@ -103,6 +105,22 @@ def load():
     lib.mt_alloc_pinned.argtypes = [ctypes.c_uint64, ctypes.POINTER(vp)]
     lib.mt_free_pinned.restype = ctypes.c_int
     lib.mt_free_pinned.argtypes = [vp]
+    lib.mt_halo_create.restype = ctypes.c_int
+    lib.mt_halo_create.argtypes = [i32, i32, i32, ctypes.POINTER(vp)]
+    lib.mt_halo_destroy.restype = None
+    lib.mt_halo_destroy.argtypes = [vp]
+    lib.mt_halo_handle.restype = ctypes.c_int
+    lib.mt_halo_handle.argtypes = [vp, ctypes.c_char_p]
+    lib.mt_halo_connect.restype = ctypes.c_int
+    lib.mt_halo_connect.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p]
+    lib.mt_halo_connect_local.restype = ctypes.c_int
+    lib.mt_halo_connect_local.argtypes = [vp, vp, vp]
+    lib.mt_halo_push.restype = ctypes.c_int
+    lib.mt_halo_push.argtypes = [vp, vp, i64, vp]
+    lib.mt_halo_pull.restype = ctypes.c_int
+    lib.mt_halo_pull.argtypes = [vp, vp, i64, vp]
+    lib.mt_halo_status.restype = ctypes.c_int
+    lib.mt_halo_status.argtypes = [vp, ctypes.POINTER(i32)]
     _lib = lib
     return lib
 

@@ -252,7 +252,11 @@ template <typename T> struct PipeArgs {
 // does not gain, and loses to the extra live state, so it keeps the static
 // round-robin schedule.
 template <typename T, int MODEL, bool FAST> struct PipeDynamic {
+#ifdef MT_DYN_ALL
+  static constexpr bool value = true;   // (experiments)
+#else
   static constexpr bool value = !(MODEL == 1 && sizeof(T) == 8);
+#endif
 };
 
 // MODEL: 0 = LWR, 1 = ARZ.  LAMK: exponent kind fixed at compile time, or

@@ -19,6 +19,7 @@
 #include "mt_direct.cuh"
 #include "mt_nonlocal.cuh"
 #include "mt_aggregate.cuh"
+#include "mt_halo.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -164,6 +165,15 @@ struct mt_engine {
   cudaEvent_t action_ready = nullptr;
   cudaStream_t stream = nullptr;
   void *d_a = nullptr, *d_b = nullptr, *d_action = nullptr, *d_reward = nullptr;
+};
+
+struct mt_halo {
+  int device = 0, dtype = MT_F64, halo = 0;
+  size_t bytes = 0;
+  void* box = nullptr;                     // my mailbox (device memory of this rank)
+  void *left = nullptr, *right = nullptr;  // the neighbours' mailboxes as mapped here
+  bool left_ipc = false, right_ipc = false;
+  unsigned pushes = 0, pulls = 0;          // exchange numbers issued so far
 };
 
 namespace {
@@ -1026,6 +1036,144 @@ int mt_debug_trace(void* dev_buf) { g_trace = (unsigned long long*)dev_buf; g_tr
 int mt_launch_count(const mt_engine* e, int64_t* out) {
   if (!e || !out) return fail(MT_EINVAL, "mt_launch_count: NULL argument");
   *out = e->launches;
+  return MT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// peer-memory halo exchange (mt_halo.cuh)
+// ---------------------------------------------------------------------------
+int mt_halo_create(int32_t device, int32_t dtype, int32_t halo, mt_halo** out) {
+  if (!out) return fail(MT_EINVAL, "mt_halo_create: NULL argument");
+  if (halo < 1 || halo > (1 << 20)) return fail(MT_EINVAL, "mt_halo_create: halo out of range");
+  if (dtype != MT_F32 && dtype != MT_F64) return fail(MT_EINVAL, "mt_halo_create: bad dtype");
+  CUDA_TRY(cudaSetDevice(device));
+  mt_halo* h = new (std::nothrow) mt_halo();
+  if (!h) return fail(MT_ENOMEM, "mt_halo_create: out of host memory");
+  h->device = device;
+  h->dtype = dtype;
+  h->halo = halo;
+  h->bytes = sizeof(HaloBox) + (size_t)8 * halo * (dtype == MT_F64 ? 8 : 4);
+  // a dedicated cudaMalloc allocation: exportable through CUDA IPC as it is
+  cudaError_t err = cudaMalloc(&h->box, h->bytes);
+  if (err == cudaSuccess) err = cudaMemset(h->box, 0, h->bytes);
+  if (err != cudaSuccess) {
+    fail(MT_ECUDA, "mt_halo_create: %s", cudaGetErrorString(err));
+    delete h;
+    return MT_ECUDA;
+  }
+  *out = h;
+  return MT_OK;
+}
+
+void mt_halo_destroy(mt_halo* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  if (h->left_ipc) cudaIpcCloseMemHandle(h->left);
+  if (h->right_ipc) cudaIpcCloseMemHandle(h->right);
+  cudaFree(h->box);
+  delete h;
+}
+
+int mt_halo_handle(const mt_halo* h, unsigned char handle_out[MT_IPC_HANDLE_BYTES]) {
+  if (!h || !handle_out) return fail(MT_EINVAL, "mt_halo_handle: NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == MT_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t ipc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaIpcGetMemHandle(&ipc, h->box));
+  memcpy(handle_out, &ipc, sizeof(ipc));
+  return MT_OK;
+}
+
+int mt_halo_connect(mt_halo* h, const unsigned char* left_handle,
+                    const unsigned char* right_handle) {
+  if (!h) return fail(MT_EINVAL, "mt_halo_connect: NULL argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaIpcMemHandle_t ipc;
+  if (left_handle) {
+    memcpy(&ipc, left_handle, sizeof(ipc));
+    CUDA_TRY(cudaIpcOpenMemHandle(&h->left, ipc, cudaIpcMemLazyEnablePeerAccess));
+    h->left_ipc = true;
+  }
+  if (right_handle) {
+    memcpy(&ipc, right_handle, sizeof(ipc));
+    CUDA_TRY(cudaIpcOpenMemHandle(&h->right, ipc, cudaIpcMemLazyEnablePeerAccess));
+    h->right_ipc = true;
+  }
+  return MT_OK;
+}
+
+int mt_halo_connect_local(mt_halo* h, mt_halo* left, mt_halo* right) {
+  if (!h) return fail(MT_EINVAL, "mt_halo_connect_local: NULL argument");
+  if ((left && (left->halo != h->halo || left->dtype != h->dtype)) ||
+      (right && (right->halo != h->halo || right->dtype != h->dtype)))
+    return fail(MT_EINVAL, "mt_halo_connect_local: neighbours differ in halo width or dtype");
+  h->left = left ? left->box : nullptr;
+  h->right = right ? right->box : nullptr;
+  return MT_OK;
+}
+
+extern "C++" {
+namespace {
+template <typename T>
+HaloArgs<T> halo_args(mt_halo* h, void* local, int64_t n_local, unsigned epoch) {
+  HaloArgs<T> a;
+  a.local = (T*)local;
+  a.n_local = n_local;
+  a.halo = h->halo;
+  a.has_left = h->left != nullptr;
+  a.has_right = h->right != nullptr;
+  a.mine = h->box;
+  a.left = h->left;
+  a.right = h->right;
+  a.epoch = epoch;
+  a.timeout_ns = 10ull * 1000ull * 1000ull * 1000ull;
+  return a;
+}
+int halo_check(mt_halo* h, void* local, int64_t n_local, const char* who) {
+  if (!h || !local) return fail(MT_EINVAL, "%s: NULL argument", who);
+  const int sides = (h->left != nullptr) + (h->right != nullptr);
+  if (n_local < (int64_t)h->halo * (sides + 1))
+    return fail(MT_EINVAL, "%s: block of %lld cells is too small for halo %d", who,
+                (long long)n_local, h->halo);
+  return MT_OK;
+}
+}  // namespace
+}  // extern "C++"
+
+int mt_halo_push(mt_halo* h, void* local, int64_t n_local, void* stream) {
+  const int rc = halo_check(h, local, n_local, "mt_halo_push");
+  if (rc != MT_OK) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const unsigned epoch = ++h->pushes;
+  if (h->dtype == MT_F64)
+    halo_push_kernel<double><<<1, 256, 0, (cudaStream_t)stream>>>(halo_args<double>(h, local, n_local, epoch));
+  else
+    halo_push_kernel<float><<<1, 256, 0, (cudaStream_t)stream>>>(halo_args<float>(h, local, n_local, epoch));
+  CUDA_TRY(cudaGetLastError());
+  return MT_OK;
+}
+
+int mt_halo_pull(mt_halo* h, void* local, int64_t n_local, void* stream) {
+  const int rc = halo_check(h, local, n_local, "mt_halo_pull");
+  if (rc != MT_OK) return rc;
+  if (h->pulls >= h->pushes) return fail(MT_ESTATE, "mt_halo_pull: no push to pair with");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const unsigned epoch = ++h->pulls;
+  if (h->dtype == MT_F64)
+    halo_pull_kernel<double><<<1, 256, 0, (cudaStream_t)stream>>>(halo_args<double>(h, local, n_local, epoch));
+  else
+    halo_pull_kernel<float><<<1, 256, 0, (cudaStream_t)stream>>>(halo_args<float>(h, local, n_local, epoch));
+  CUDA_TRY(cudaGetLastError());
+  return MT_OK;
+}
+
+int mt_halo_status(mt_halo* h, int32_t* timed_out) {
+  if (!h || !timed_out) return fail(MT_EINVAL, "mt_halo_status: NULL argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  HaloBox box;
+  CUDA_TRY(cudaMemcpy(&box, h->box, sizeof(box), cudaMemcpyDeviceToHost));
+  *timed_out = box.error ? 1 : 0;
   return MT_OK;
 }
 

@@ -57,6 +57,7 @@ class DomainDecomposedRoad(object):
         self.n_local = (self.hi - self.lo) + halo * (self.has_left + self.has_right)
         self.stepper = stepper
         self.exchange = exchange or self._torch_exchange
+        self.peer = None               # a PeerHalo: exchange over peer memory instead
         self._since_exchange = 0
 
     # ------------------------------------------------------------------ #
@@ -96,6 +97,29 @@ class DomainDecomposedRoad(object):
         self._since_exchange += 1
         return out
 
+    def advance(self, local_obs, n_steps):
+        """``n_steps`` global time steps.  Between two exchanges the ghosts
+        allow ``halo`` steps; when the stepper offers ``block(local_obs, k,
+        bc_left, bc_right)`` (``engine_stepper`` does: one ``mt_rollout`` call,
+        k back-to-back launches) each such run of steps is one call instead of
+        k Python round trips."""
+        block = getattr(self.stepper, "block", None)
+        left = int(n_steps)
+        while left > 0:
+            if self.needs_refresh():
+                local_obs = self.refresh(local_obs)
+            k = min(left, self.halo - self._since_exchange)
+            bl = "halo" if self.has_left else "physical"
+            br = "halo" if self.has_right else "physical"
+            if block is not None:
+                local_obs = block(local_obs, k, bl, br)
+            else:
+                for _ in range(k):
+                    local_obs = self.stepper(local_obs, bl, br)
+            self._since_exchange += k
+            left -= k
+        return local_obs
+
     def edge_cells(self, local_obs):
         """``(send_left, send_right)``: my first / last ``halo`` own cells as
         ``[rho(h) | v(h)]`` (None on a true road end)."""
@@ -124,6 +148,10 @@ class DomainDecomposedRoad(object):
 
     def refresh(self, local_obs):
         """Swap edge cells with the neighbours."""
+        if self.peer is not None:      # peer-memory mailboxes: in place, on the GPU
+            self.peer.exchange(local_obs, self.n_local)
+            self._since_exchange = 0
+            return local_obs
         send_l, send_r = self.edge_cells(local_obs)
         recv_l, recv_r = self.exchange(send_l, send_r)
         return self.set_ghosts(local_obs, recv_l, recv_r)
@@ -170,6 +198,86 @@ class DomainDecomposedRoad(object):
         return torch.cat(rhos + vs)
 
 
+class PeerHalo(object):
+    """Ghost-cell exchange through peer-mapped mailboxes (``mt_halo_*``): the
+    edge cells travel as plain NVLink stores of a small kernel, a second small
+    kernel waits for the neighbours' flags and fills the ghosts -- no NCCL and
+    no host round trip on the data path.  One object per rank; every rank must
+    call ``exchange`` the same number of times.
+
+    ``PeerHalo(halo, dtype, device).connect_group(rank, world)`` wires the
+    ranks of a ``torch.distributed`` group together (the 64-byte IPC handles
+    travel through ``all_gather_object``); ``PeerHalo.connect_local`` wires
+    objects living in one process (tests)."""
+
+    def __init__(self, halo, dtype, device=0):
+        import ctypes
+        from mbrl_traffic_b200 import _lib
+        from mbrl_traffic_b200.engine import _DTYPES, dtype_name
+        self._lib = _lib.load()
+        self._check = _lib.check
+        self.halo, self.device = int(halo), int(device)
+        h = ctypes.c_void_p()
+        self._check(self._lib.mt_halo_create(self.device, _DTYPES[dtype_name(dtype)], self.halo,
+                                             ctypes.byref(h)))
+        self._h = h
+
+    def handle(self):
+        import ctypes
+        buf = ctypes.create_string_buffer(64)
+        self._check(self._lib.mt_halo_handle(self._h, buf))
+        return buf.raw
+
+    def connect_group(self, rank, world, group=None):
+        import torch.distributed as dist
+        handles = [None] * world
+        dist.all_gather_object(handles, self.handle(), group=group)
+        left = handles[rank - 1] if rank > 0 else None
+        right = handles[rank + 1] if rank < world - 1 else None
+        self._check(self._lib.mt_halo_connect(self._h, left, right))
+        return self
+
+    @staticmethod
+    def connect_local(halos):
+        """Wire ``halos[r]`` (same process, rank order) to their neighbours."""
+        for r, h in enumerate(halos):
+            left = halos[r - 1]._h if r > 0 else None
+            right = halos[r + 1]._h if r < len(halos) - 1 else None
+            h._check(h._lib.mt_halo_connect_local(h._h, left, right))
+        return halos
+
+    def push(self, local_obs, n_local, stream=None):
+        from mbrl_traffic_b200.engine import _ptr, _stream_ptr
+        self._check(self._lib.mt_halo_push(self._h, _ptr(local_obs), int(n_local),
+                                           _stream_ptr(stream)))
+
+    def pull(self, local_obs, n_local, stream=None):
+        from mbrl_traffic_b200.engine import _ptr, _stream_ptr
+        self._check(self._lib.mt_halo_pull(self._h, _ptr(local_obs), int(n_local),
+                                           _stream_ptr(stream)))
+
+    def exchange(self, local_obs, n_local, stream=None):
+        self.push(local_obs, n_local, stream)
+        self.pull(local_obs, n_local, stream)
+
+    def timed_out(self):
+        import ctypes
+        flag = ctypes.c_int32(0)
+        self._check(self._lib.mt_halo_status(self._h, ctypes.byref(flag)))
+        return bool(flag.value)
+
+    def close(self):
+        if self._h:
+            self._lib.mt_halo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _all_gather_ragged(parts, mine, rank, world):
     import torch.distributed as dist
     for r in range(world):
@@ -205,7 +313,7 @@ def engine_stepper(engine, physical_left, physical_right, left_val=(0.0, 0.0),
     from mbrl_traffic_b200 import _lib
     state = {"bc": None, "buf": None}
 
-    def step(local_obs, bc_left, bc_right):
+    def prepare(local_obs, bc_left, bc_right):
         cl = _lib.MT_BC_HALO if bc_left == "halo" else physical_left
         cr = _lib.MT_BC_HALO if bc_right == "halo" else physical_right
         if state["bc"] != (cl, cr):
@@ -216,9 +324,19 @@ def engine_stepper(engine, physical_left, physical_right, left_val=(0.0, 0.0),
         x = local_obs.reshape(1, -1)
         if state["buf"] is None or state["buf"].data_ptr() == x.data_ptr():
             state["buf"] = torch.empty_like(x)
-        out = state["buf"]
+        return x, state["buf"]
+
+    def step(local_obs, bc_left, bc_right):
+        x, out = prepare(local_obs, bc_left, bc_right)
         engine.step(x, out)
         state["buf"] = x          # ping-pong
         return out.reshape(local_obs.shape)
 
+    def block(local_obs, k, bc_left, bc_right):
+        x, other = prepare(local_obs, bc_left, bc_right)
+        final = engine.rollout(x, other, k)
+        state["buf"] = other if final.data_ptr() == x.data_ptr() else x
+        return final.reshape(local_obs.shape)
+
+    step.block = block
     return step

@@ -118,3 +118,38 @@ def test_decomposed_road_two_ranks_gloo(kind, halo):
     for _ in range(steps):
         ref = fn(ref, boundary_conditions="extend_both")
     assert np.array_equal(got, ref)
+
+
+def test_advance_runs_whole_blocks_and_refreshes():
+    """advance(n) == n x step(); a stepper offering ``block`` gets one call per
+    run of steps between exchanges."""
+    n, halo, steps = 120, 4, 11
+    road = _make_road(n, seed=9)
+
+    def exchange(send_l, send_r):
+        return None, None
+
+    base = _oracle_stepper("lwr", "extend_both")
+    d1 = DomainDecomposedRoad(n, 0, 1, halo, base, exchange=exchange)
+    ref = d1.scatter(road)
+    for _ in range(steps):
+        ref = d1.step(ref)
+
+    blocks = []
+
+    def stepper(x, bl, br):
+        return base(x, bl, br)
+
+    def block(x, k, bl, br):
+        blocks.append(k)
+        for _ in range(k):
+            x = base(x, bl, br)
+        return x
+
+    stepper.block = block
+    d2 = DomainDecomposedRoad(n, 0, 1, halo, stepper, exchange=exchange)
+    out = d2.advance(d2.scatter(road), steps)
+    assert np.array_equal(out, ref)
+    assert blocks == [4, 4, 3]
+    d2.advance(out, 2)                # finishes the open block first: 1 + 1
+    assert blocks == [4, 4, 3, 1, 1]

@@ -690,6 +690,106 @@ def test_domain_decomposition_emulated(kind, world, halo, n):
     assert np.array_equal(np.concatenate((rho, v)), ref)
 
 
+@pytest.mark.parametrize("kind", ["lwr", "arz"])
+@pytest.mark.parametrize("world,halo,n", [(2, 4, 4096), (4, 8, 40000)])
+def test_domain_decomposition_block_rollout(kind, world, halo, n):
+    """The steps between two exchanges as ONE ``mt_rollout`` call per rank
+    (``engine_stepper(...).block``; short blocks take the fused multi-step
+    kernel with the HALO pass-through rule): same cells as the whole road."""
+    _need_gpu()
+    from mbrl_traffic_b200 import _lib
+    from mbrl_traffic_b200.dist import DomainDecomposedRoad, engine_stepper
+    from mbrl_traffic_b200.engine import Engine
+    steps = 5 * halo
+    params = dict(dx=50, dt=0.5, rho_max=1, v_max=30, lam=1, tau=9)
+    road = make_obs(1, n, seed=33)[0]
+    cur = road
+    for _ in range(steps):
+        cur = oracle_step(kind, cur, boundary_conditions="extend_both")
+    ranks, local = [], []
+    for r in range(world):
+        d = DomainDecomposedRoad(n, r, world, halo, None, exchange=lambda *_: (None, None))
+        eng = Engine(kind, "float64", 1, d.n_local)
+        d.stepper = engine_stepper(eng, _lib.MT_BC_EXTEND, _lib.MT_BC_EXTEND, **params)
+        ranks.append(d)
+        local.append(d.scatter(gpu(road)).clone())
+    for blk in range(steps // halo):
+        if blk > 0:
+            edges = [d.edge_cells(x) for d, x in zip(ranks, local)]
+            for r, d in enumerate(ranks):
+                d.set_ghosts(local[r],
+                             edges[r - 1][1] if d.has_left else None,
+                             edges[r + 1][0] if d.has_right else None)
+        local = [d.stepper.block(x, halo, "halo" if d.has_left else "physical",
+                                 "halo" if d.has_right else "physical")
+                 for d, x in zip(ranks, local)]
+    torch.cuda.synchronize()
+    rho = torch.cat([d.own(x)[0] for d, x in zip(ranks, local)]).cpu().numpy()
+    v = torch.cat([d.own(x)[1] for d, x in zip(ranks, local)]).cpu().numpy()
+    assert np.array_equal(np.concatenate((rho, v)), cur)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("world,halo,n", [(2, 4, 4096), (4, 8, 40000), (3, 1, 3000)])
+def test_peer_halo_mailboxes_emulated(dtype, world, halo, n):
+    """mt_halo_push / mt_halo_pull with all ranks in one process (mailboxes
+    wired with mt_halo_connect_local; every push is issued before any pull, so
+    no kernel ever waits): the decomposed road equals the whole road."""
+    _need_gpu()
+    from mbrl_traffic_b200 import _lib
+    from mbrl_traffic_b200.dist import DomainDecomposedRoad, PeerHalo, engine_stepper
+    from mbrl_traffic_b200.engine import Engine
+    kind = "arz"
+    steps = 4 * halo
+    params = dict(dx=50, dt=0.5, rho_max=1, v_max=30, lam=1, tau=9)
+    road = make_obs(1, n, seed=35, dtype=dtype)[0]
+    name = np.dtype(dtype).name
+    full = Engine(kind, name, 1, n)
+    full.set_params(boundary_conditions="extend_both", **params)
+    a = gpu(road).reshape(1, -1).clone()
+    ref = full.rollout(a, torch.empty_like(a), steps).cpu().numpy()[0]
+    ranks, local = [], []
+    for r in range(world):
+        d = DomainDecomposedRoad(n, r, world, halo, None)
+        eng = Engine(kind, name, 1, d.n_local)
+        d.stepper = engine_stepper(eng, _lib.MT_BC_EXTEND, _lib.MT_BC_EXTEND, **params)
+        ranks.append(d)
+        local.append(d.scatter(gpu(road)).clone())
+    halos = PeerHalo.connect_local([PeerHalo(halo, name, 0) for _ in range(world)])
+    for blk in range(steps // halo):
+        if blk > 0:
+            for h, d, x in zip(halos, ranks, local):
+                h.push(x, d.n_local)
+            for h, d, x in zip(halos, ranks, local):
+                h.pull(x, d.n_local)
+        local = [d.stepper.block(x, halo, "halo" if d.has_left else "physical",
+                                 "halo" if d.has_right else "physical")
+                 for d, x in zip(ranks, local)]
+    torch.cuda.synchronize()
+    assert not any(h.timed_out() for h in halos)
+    rho = torch.cat([d.own(x)[0] for d, x in zip(ranks, local)]).cpu().numpy()
+    v = torch.cat([d.own(x)[1] for d, x in zip(ranks, local)]).cpu().numpy()
+    assert np.array_equal(np.concatenate((rho, v)), ref)
+    for h in halos:
+        h.close()
+
+
+def test_peer_halo_argument_checks():
+    _need_gpu()
+    from mbrl_traffic_b200.dist import PeerHalo
+    with pytest.raises(ValueError):
+        PeerHalo(0, "float64", 0)
+    a, b = PeerHalo.connect_local([PeerHalo(4, "float64", 0), PeerHalo(4, "float64", 0)])
+    x = torch.zeros(2 * 6, dtype=torch.float64, device="cuda:0")
+    with pytest.raises(ValueError):       # block narrower than halo + own cells
+        a.push(x, 6)
+    y = torch.zeros(2 * 64, dtype=torch.float64, device="cuda:0")
+    with pytest.raises(Exception):        # pull without a matching push
+        a.pull(y, 64)
+    a.close()
+    b.close()
+
+
 # --------------------------------------------------------------------------- #
 # edge cases: zeros, NaNs, equilibrium, tiny and ragged shapes                #
 # --------------------------------------------------------------------------- #

@@ -19,7 +19,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mbrl_traffic_b200 import _lib  # noqa: E402
-from mbrl_traffic_b200.dist import (DomainDecomposedRoad, engine_stepper,  # noqa: E402
+from mbrl_traffic_b200.dist import (DomainDecomposedRoad, PeerHalo, engine_stepper,  # noqa: E402
                                     shard_range)
 from mbrl_traffic_b200.engine import Engine  # noqa: E402
 
@@ -71,22 +71,31 @@ def main():
     d = DomainDecomposedRoad(n_road, rank, world, halo, None)
     eng = Engine("arz", "float64", 1, d.n_local, device=local_rank)
     d.stepper = engine_stepper(eng, _lib.MT_BC_EXTEND, _lib.MT_BC_EXTEND, **PARAMS)
-    local = d.scatter(road).clone()
-    for _ in range(2 * halo + 1):             # warm-up incl. two exchanges (NCCL set-up)
-        local = d.step(local)
-    local = d.scatter(road).clone()
-    d._since_exchange = 0
-    dist.barrier()
-    torch.cuda.synchronize()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        local = d.step(local)
-    e1.record()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    peer = PeerHalo(halo, "float64", local_rank).connect_group(rank, world)
+
+    def timed_run(use_peer):
+        d.peer = peer if use_peer else None
+        x = d.scatter(road).clone()
+        d._since_exchange = 0
+        x = d.advance(x, 2 * halo + 1)        # warm-up incl. two exchanges (NCCL set-up)
+        x = d.scatter(road).clone()
+        d._since_exchange = 0
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        x = d.advance(x, steps)               # one mt_rollout call per run of `halo` steps
+        e1.record()
+        torch.cuda.synchronize()
+        tt = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return x, float(tt.item())
+
+    local_nccl, t_nccl = timed_run(False)
+    local, t_peer = timed_run(True)
+    report["peer_halo_timed_out"] = bool(peer.timed_out())
+    report["peer_equals_nccl"] = bool(torch.equal(local, local_nccl))
     full = d.gather(local)
     single = Engine("arz", "float64", 1, n_road, device=local_rank)
     single.set_params(boundary_conditions="extend_both", **PARAMS)
@@ -98,13 +107,15 @@ def main():
     report["road_cells"] = n_road
     report["halo"] = halo
     report["road_identical_to_single_gpu"] = bool(torch.equal(full, ref.reshape(-1)))
-    report["road_cell_updates_per_s"] = n_road * steps / float(t.item())
+    report["road_cell_updates_per_s"] = n_road * steps / t_peer
+    report["road_cell_updates_per_s_nccl_halo"] = n_road * steps / t_nccl
     report["single_gpu_cell_updates_per_s"] = n_road * steps / t_single
     if rank == 0:
         print(json.dumps(report), flush=True)
     dist.barrier()
     dist.destroy_process_group()
-    ok = report["sharded_bit_identical"] and report["road_identical_to_single_gpu"]
+    ok = (report["sharded_bit_identical"] and report["road_identical_to_single_gpu"]
+          and report["peer_equals_nccl"] and not report["peer_halo_timed_out"])
     sys.exit(0 if ok else 1)
 
 
