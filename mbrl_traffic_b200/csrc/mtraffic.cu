@@ -163,6 +163,9 @@ struct mt_engine {
   static constexpr int HOST_STREAMS = 3;
   cudaStream_t hs[HOST_STREAMS] = {nullptr, nullptr, nullptr};
   cudaEvent_t action_ready = nullptr;
+  // per-chunk hand-offs: upload stream -> compute stream -> download stream
+  static constexpr int MAX_CHUNKS = 80;
+  cudaEvent_t ev_up[MAX_CHUNKS] = {}, ev_done[MAX_CHUNKS] = {};
   cudaStream_t stream = nullptr;
   void *d_a = nullptr, *d_b = nullptr, *d_action = nullptr, *d_reward = nullptr;
 };
@@ -768,6 +771,10 @@ int mt_create(const mt_config* cfg, mt_engine** out) {
     for (int i = 0; i < mt_engine::HOST_STREAMS && err == cudaSuccess; ++i)
       err = cudaStreamCreateWithFlags(&e->hs[i], cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->action_ready, cudaEventDisableTiming);
+    for (int i = 0; i < mt_engine::MAX_CHUNKS && err == cudaSuccess; ++i) {
+      err = cudaEventCreateWithFlags(&e->ev_up[i], cudaEventDisableTiming);
+      if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming);
+    }
     if (err == cudaSuccess) err = cudaMalloc(&e->d_a, B * 2 * N * e->elt);
     if (err == cudaSuccess) err = cudaMalloc(&e->d_b, B * 2 * N * e->elt);
     if (err == cudaSuccess) err = cudaMalloc(&e->d_action, B * e->elt);
@@ -798,6 +805,10 @@ void mt_destroy(mt_engine* e) {
   for (int i = 0; i < mt_engine::HOST_STREAMS; ++i)
     if (e->hs[i]) cudaStreamDestroy(e->hs[i]);
   if (e->action_ready) cudaEventDestroy(e->action_ready);
+  for (int i = 0; i < mt_engine::MAX_CHUNKS; ++i) {
+    if (e->ev_up[i]) cudaEventDestroy(e->ev_up[i]);
+    if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
+  }
   if (e->params_ready) cudaEventDestroy(e->params_ready);
   delete e;
 }
@@ -908,8 +919,10 @@ int mt_step_host(mt_engine* e, const void* obs_in_host, const void* action_host,
   const size_t row_bytes = 2 * N * e->elt;
   constexpr int NS = mt_engine::HOST_STREAMS;
   // Roads are independent, so the batch is cut into chunks that flow through
-  // upload -> n_steps kernels -> download on NS streams: PCIe carries both
-  // directions at once and the kernels hide behind the copies.
+  // upload -> n_steps kernels -> download, each stage on its own stream
+  // (hs[0], hs[1], hs[2]) with one event per chunk between stages: the two
+  // copy engines never wait for each other, PCIe carries both directions at
+  // once and the kernels hide behind the copies.
   static long long chunk_bytes = 0;
   if (chunk_bytes == 0) {
     const char* s = getenv("MT_HOST_CHUNK_MB");
@@ -921,6 +934,30 @@ int mt_step_host(mt_engine* e, const void* obs_in_host, const void* action_host,
   if (n_chunks > 64) n_chunks = 64;
   if (n_chunks > B) n_chunks = B;
   const long long per = (B + n_chunks - 1) / n_chunks;
+  // Chunk plan.  Nothing comes back before the first chunk is up, and nothing
+  // goes up while the last one comes back: the first and last chunks are small
+  // (per/8, per/4, per/2) so that this fill and drain cost little, the middle
+  // ones are full-size so that the per-copy overheads stay amortised.
+  long long plan_n[mt_engine::MAX_CHUNKS];
+  int n_plan = 0;
+  {
+    long long left = B;
+    long long ramp[3] = {per >> 3, per >> 2, per >> 1};
+    static const bool want_graded = !(getenv("MT_HOST_GRADED") && atoi(getenv("MT_HOST_GRADED")) == 0);
+    const bool graded = want_graded && n_chunks >= 4 && ramp[0] >= 1;
+    long long tail[3] = {0, 0, 0};
+    if (graded) {
+      for (int i = 0; i < 3; ++i) { plan_n[n_plan++] = ramp[i]; left -= ramp[i]; }
+      for (int i = 0; i < 3; ++i) { tail[i] = ramp[2 - i]; left -= tail[i]; }
+    }
+    while (left > 0) {
+      const long long n = left < per ? left : per;
+      plan_n[n_plan++] = n;
+      left -= n;
+    }
+    if (graded)
+      for (int i = 0; i < 3; ++i) plan_n[n_plan++] = tail[i];
+  }
   for (int i = 0; i < NS; ++i) CUDA_TRY(cudaStreamWaitEvent(e->hs[i], e->params_ready, 0));
   e->params_pending = false;
   if (action_host) {
@@ -934,14 +971,15 @@ int mt_step_host(mt_engine* e, const void* obs_in_host, const void* action_host,
   const bool fuse = n_steps >= 2 && can_fuse_steps(e, e->d_a, e->d_b);
   const bool odd = (n_steps & 1) != 0;
   char* result = (char*)((odd || fuse) ? e->d_b : e->d_a);
-  for (long long c = 0; c < n_chunks; ++c) {
-    const long long env0 = c * per;
-    const long long n_env = (env0 + per <= B) ? per : B - env0;
-    if (n_env <= 0) break;
-    cudaStream_t s = e->hs[c % NS];
+  cudaStream_t s_up = e->hs[0], s = e->hs[1], s_down = e->hs[2];
+  long long env0 = 0;
+  for (int c = 0; c < n_plan; env0 += plan_n[c], ++c) {
+    const long long n_env = plan_n[c];
     const size_t off = (size_t)env0 * row_bytes, bytes = (size_t)n_env * row_bytes;
     CUDA_TRY(cudaMemcpyAsync((char*)e->d_a + off, (const char*)obs_in_host + off, bytes,
-                             cudaMemcpyHostToDevice, s));
+                             cudaMemcpyHostToDevice, s_up));
+    CUDA_TRY(cudaEventRecord(e->ev_up[c], s_up));
+    CUDA_TRY(cudaStreamWaitEvent(s, e->ev_up[c], 0));
     void* cur = e->d_a;
     void* nxt = e->d_b;
     if (fuse) {
@@ -958,12 +996,14 @@ int mt_step_host(mt_engine* e, const void* obs_in_host, const void* action_host,
         void* tmp = cur; cur = nxt; nxt = tmp;
       }
     }
+    CUDA_TRY(cudaEventRecord(e->ev_done[c], s));
+    CUDA_TRY(cudaStreamWaitEvent(s_down, e->ev_done[c], 0));
     CUDA_TRY(cudaMemcpyAsync((char*)obs_out_host + off, result + off, bytes,
-                             cudaMemcpyDeviceToHost, s));
+                             cudaMemcpyDeviceToHost, s_down));
     if (reward_out_host)
       CUDA_TRY(cudaMemcpyAsync((char*)reward_out_host + (size_t)env0 * e->elt,
                                (char*)e->d_reward + (size_t)env0 * e->elt,
-                               (size_t)n_env * e->elt, cudaMemcpyDeviceToHost, s));
+                               (size_t)n_env * e->elt, cudaMemcpyDeviceToHost, s_down));
   }
   for (int i = 0; i < NS; ++i) CUDA_TRY(cudaStreamSynchronize(e->hs[i]));
   return MT_OK;

@@ -41,8 +41,22 @@ for _ in range(10):
     ho.copy_(x, non_blocking=True)
 torch.cuda.synchronize()
 d2h = (time.perf_counter() - t0) / 10
+# both directions at once (two streams): the ceiling of the pipelined host path
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+y = torch.empty_like(x)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(10):
+    with torch.cuda.stream(s1):
+        x.copy_(h, non_blocking=True)
+    with torch.cuda.stream(s2):
+        ho.copy_(y, non_blocking=True)
+torch.cuda.synchronize()
+bidir = (time.perf_counter() - t0) / 10
 print(json.dumps(dict(chunk_mb=os.environ.get("MT_HOST_CHUNK_MB", "8"),
                       ms_per_step=round(dt * 1e3, 3),
                       gcups=round(b * n / dt / 1e9, 3),
                       h2d_GBps=round(x.numel() * 8 / h2d / 1e9, 1),
-                      d2h_GBps=round(x.numel() * 8 / d2h / 1e9, 1))))
+                      d2h_GBps=round(x.numel() * 8 / d2h / 1e9, 1),
+                      bidir_GBps_each=round(x.numel() * 8 / bidir / 1e9, 1),
+                      bidir_ms=round(bidir * 1e3, 3))))
