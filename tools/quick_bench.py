@@ -38,6 +38,9 @@ def main():
                     help="pass the parameters as per-road device arrays")
     ap.add_argument("--rho-max", type=float, default=1.0)
     ap.add_argument("--lam", type=float, default=1.0)
+    ap.add_argument("--bc", default="loop",
+                    help="loop | extend_both | inflow_outflow (constant 0.3 rho_max inflow, "
+                         "free outflow: BASELINE config 3)")
     ap.add_argument("--population", action="store_true",
                     help="one random parameter vector per road (an optimizer's population)")
     args = ap.parse_args()
@@ -54,16 +57,17 @@ def main():
         if not args.per_env:
             return x
         return torch.full((b,), float(x), dtype=tdt, device="cuda")
+    bc = {"inflow_outflow": 0.3 * args.rho_max} if args.bc == "inflow_outflow" else args.bc
     if args.population:
         g = torch.Generator(device="cuda").manual_seed(1)
         def rnd(lo, hi):
             return lo + (hi - lo) * torch.rand(b, generator=g, dtype=tdt, device="cuda")
         eng.set_params(dx=50, dt=0.5, rho_max=rnd(0.9, 1.5) * args.rho_max, v_max=rnd(20, 40),
-                       lam=rnd(0.5, 3.0), boundary_conditions="loop", tau=rnd(5, 25),
+                       lam=rnd(0.5, 3.0), boundary_conditions=bc, tau=rnd(5, 25),
                        fast_math=args.fast, no_pipeline=args.direct, gamma=gamma)
     else:
         eng.set_params(dx=50, dt=0.5, rho_max=par(args.rho_max), v_max=par(30),
-                       lam=par(args.lam), boundary_conditions="loop", tau=par(9),
+                       lam=par(args.lam), boundary_conditions=bc, tau=par(9),
                        fast_math=args.fast, no_pipeline=args.direct, gamma=gamma)
     rng = np.random.default_rng(0)
     rho = args.rho_max * rng.uniform(0.05, 0.9, (b, n))

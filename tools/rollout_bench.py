@@ -1,9 +1,14 @@
 """Config 5: feed-forward policy driving a batched ARZ ensemble.
 
     python tools/rollout_bench.py [--envs 4096] [--cells 1000] [--horizon 500]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 \
+        --master-addr 127.0.0.1 --master-port 29521 tools/rollout_bench.py
 
 Reports road-steps/s and cell-updates/s of the whole loop (policy MLP +
-model step + reward), CUDA-graph replayed, and of K-shoot planning.
+model step + reward), CUDA-graph replayed, and of K-shoot planning.  Under
+torchrun every rank drives its own `--envs` roads with a replica of the policy
+(env-sharded, no data-path collective); the times are the max over ranks and
+the rates the whole job's.
 """
 import argparse
 import json
@@ -28,13 +33,28 @@ def main():
     ap.add_argument("--dtype", default="float64")
     ap.add_argument("--actor-dtype", default="bfloat16")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def slowest(seconds):
+        if world == 1:
+            return seconds
+        t = torch.tensor([seconds], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     tdt = torch.float64 if args.dtype == "float64" else torch.float32
     b, n = args.envs, args.cells
     p = dict(ARZ_MODEL_PARAMS)
     p.pop("optimizer_cls")
     model = ARZModel(None, None, None, None, 0, optimizer_cls=None,
-                     action_is_speed_limit=True, **p)
-    rng = np.random.default_rng(0)
+                     action_is_speed_limit=True, device=local_rank, **p)
+    rng = np.random.default_rng(rank)
     rho = rng.uniform(0.05, 0.9, (b, n))
     v = 30 * (1 - rho) + rng.normal(0, 1, (b, n))
     obs = torch.as_tensor(np.concatenate((rho, v), 1), device="cuda").to(tdt)
@@ -47,10 +67,10 @@ def main():
         t0 = time.perf_counter()
         total = policy_rollout(env, actor, obs, use_graph=graph)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        dt = slowest(time.perf_counter() - t0)
         out["graph" if graph else "eager"] = dict(
-            seconds=round(dt, 4), road_steps_per_s=b * args.horizon / dt,
-            cell_updates_per_s=b * n * args.horizon / dt,
+            seconds=round(dt, 4), road_steps_per_s=world * b * args.horizon / dt,
+            cell_updates_per_s=world * b * n * args.horizon / dt,
             mean_return=float(total.mean()))
     k, h = 16, 10
     pol = KShootPolicy(model, b // k, n, num_particles=k, traj_length=h, dtype=tdt)
@@ -60,12 +80,16 @@ def main():
     for _ in range(10):
         pol.get_action(obs[:b // k])
     torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / 10
-    out["kshoot"] = dict(roads=b // k, particles=k, traj_length=h,
-                         plans_per_s=(b // k) / dt,
-                         cell_updates_per_s=b * n * h / dt)
-    print(json.dumps(dict(envs=b, cells=n, horizon=args.horizon,
-                          dtype=args.dtype, actor_dtype=args.actor_dtype, **out)))
+    dt = slowest((time.perf_counter() - t0) / 10)
+    out["kshoot"] = dict(roads=world * (b // k), particles=k, traj_length=h,
+                         plans_per_s=world * (b // k) / dt,
+                         cell_updates_per_s=world * b * n * h / dt)
+    if rank == 0:
+        print(json.dumps(dict(n_gpus=world, envs_per_gpu=b, cells=n, horizon=args.horizon,
+                              dtype=args.dtype, actor_dtype=args.actor_dtype, **out)))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
