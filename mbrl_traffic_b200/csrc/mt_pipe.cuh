@@ -606,11 +606,18 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
         }
         if (active && row_first) a.reward[env] = num / den;
       } else {
-        for (int off = 16; off > 0; off >>= 1) {
-          num += __shfl_xor_sync(full, num, off);
-          den += __shfl_xor_sync(full, den, off);
+        // Shuffles are the cost of this reduction (one warp-wide SHFL per clock
+        // and SM), so the two sums share one butterfly: in the first round even
+        // lanes keep the numerator and odd lanes the denominator of the pair,
+        // the other four rounds then move ONE value per lane.  Lane 0 ends up
+        // with the warp's numerator, lane 1 with its denominator.
+        {
+          const bool odd = (t & 1) != 0;
+          T acc = (odd ? den : num) + __shfl_xor_sync(full, odd ? num : den, 1);
+          for (int off = 2; off <= 16; off <<= 1) acc += __shfl_xor_sync(full, acc, off);
+          if ((t & 31) == 0) sm.s_num[t >> 5] = acc;
+          if ((t & 31) == 1) sm.s_den[t >> 5] = acc;
         }
-        if (lane0) { sm.s_num[t >> 5] = num; sm.s_den[t >> 5] = den; }
         consumer_sync(NC);
         if (active && row_first) {
           const int w0 = t >> 5, nw = a.tpe >> 5;
