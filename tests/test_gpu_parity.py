@@ -213,6 +213,38 @@ def test_dynamic_tile_schedule_bit_exact(b, n, bci):
     m.close()
 
 
+def test_dynamic_tile_schedule_with_action_reward_and_table():
+    """The drawn tile decides which road's speed limit, parameter row and
+    reward slot a consumer uses: check all three on a dynamically scheduled
+    batch (LWR, 4800 roads), with per-road parameters on top."""
+    _need_gpu()
+    from mbrl_traffic_b200.engine import Engine
+    b, n = 4800, 1000
+    rng = np.random.default_rng(77)
+    obs = make_obs(b, n, seed=44)
+    act = rng.uniform(10.0, 30.0, b)
+    eng = Engine("lwr", "float64", b, n)
+    eng.set_params(dx=50, dt=0.5, rho_max=1, v_max=30, lam=1, boundary_conditions="loop")
+    x = gpu(obs)
+    out = torch.empty_like(x)
+    rew = torch.empty(b, dtype=torch.float64, device="cuda:0")
+    eng.step(x, out, action=gpu(act), reward=rew)
+    ref = o.lwr_step(obs, v_max=act)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    np.testing.assert_allclose(rew.cpu().numpy(), o.mean_speed_reward(ref), rtol=1e-12)
+    # per-road parameter table
+    rho_max = rng.choice([1.0, 0.5, 0.7], b)
+    lam = rng.choice([1.0, 2.0], b)
+    obs2 = obs.copy()
+    obs2[:, :n] *= rho_max[:, None]
+    eng.set_params(dx=50, dt=0.5, rho_max=gpu(rho_max), v_max=gpu(act), lam=gpu(lam),
+                   boundary_conditions="loop")
+    eng.step(gpu(obs2), out)
+    ref2 = o.lwr_step(obs2, rho_max=rho_max, v_max=act, lam=lam)
+    assert np.array_equal(out.cpu().numpy(), ref2)
+    eng.close()
+
+
 def test_dynamic_tile_schedule_f32_fast():
     _need_gpu()
     obs32 = make_obs(4800, 1000, seed=21, dtype=np.float32)
