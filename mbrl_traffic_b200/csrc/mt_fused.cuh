@@ -181,6 +181,17 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_fused_ker
     }
 
     T num = 0, den = 0;
+    // a reward row per inner step (mt_rollout with rewards): each warp leaves its
+    // sums in r_num/r_den[j & 1]; the road's first thread finishes step j after
+    // the exchange barrier of step j + 1 (or after the loop), so the per-step
+    // reduction costs no barrier of its own
+    const bool every = want_reward && a.reward_stride > 0;
+    auto reward_finish = [&](int j) {
+      const int w0 = t >> 5, nw = a.tpe >> 5;   // (roads wider than a warp only)
+      T n = sm.r_num[j & 1][w0], d = sm.r_den[j & 1][w0];
+      for (int w = 1; w < nw; ++w) { n += sm.r_num[j & 1][w0 + w]; d += sm.r_den[j & 1][w0 + w]; }
+      a.reward[(size_t)j * (size_t)a.reward_stride + env] = n / d;
+    };
     // n_inner model steps on this tile; between them the state lives in
     // registers and only the edge values cross threads
     for (int j = 0; j < n_inner; ++j) {
@@ -219,6 +230,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_fused_ker
       consumer_sync(NC);                               // exchange visible
       if (j == 0 && lane0) mbar_arrive(empty0 + 8 * s);  // stage s fully read: release it
       if (last) mbar_wait(ofree0 + 8 * o, ph_out ^ 1);   // output stage drained by its last store
+      if (every && a.tpe > 32 && j > 0 && active && row_first) reward_finish(j - 1);
 
       if (active) {
         const T S_right = xS[xi + 1], D_left = xD[xi], r_left = xR[xi];
@@ -231,7 +243,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_fused_ker
 #pragma unroll
           for (int k = 0; k < CPT; ++k) { rho[k] = rn[k]; v[k] = vn[k]; }
         } else {
-          if (want_reward) {
+          if (want_reward && !every) {
 #pragma unroll
             for (int k = 0; k < CPT; ++k) { num += rn[k] * vn[k]; den += rn[k]; }
           }
@@ -246,12 +258,45 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_fused_ker
           }
         }
       }
+      if (every) {
+        // this step's sum(rho v) and sum(rho) over my cells, then over the warp
+        // (or over the road's lanes when a road is narrower than a warp): the
+        // two sums share one butterfly, see step_pipe_kernel
+        T pn = 0, pd = 0;
+        if (active) {
+#pragma unroll
+          for (int k = 0; k < CPT; ++k) { pn += rn[k] * vn[k]; pd += rn[k]; }
+        }
+        const unsigned full = 0xffffffffu;
+        const int width = a.tpe <= 32 ? a.tpe : 32;
+        if (width >= 2) {
+          const bool odd = (t & 1) != 0;
+          T acc = (odd ? pd : pn) + __shfl_xor_sync(full, odd ? pn : pd, 1);
+          for (int off = 2; off < width; off <<= 1) acc += __shfl_xor_sync(full, acc, off);
+          if (a.tpe <= 32) {
+            // lanes 0 / 1 of the road's group hold its two sums: hand the
+            // denominator to the first lane, which stores the reward itself
+            const T dsum = __shfl_down_sync(full, acc, 1);
+            if (active && row_first)
+              a.reward[(size_t)j * (size_t)a.reward_stride + env] = acc / dsum;
+          } else {
+            if ((t & 31) == 0) sm.r_num[j & 1][t >> 5] = acc;
+            if ((t & 31) == 1) sm.r_den[j & 1][t >> 5] = acc;
+          }
+        } else if (active) {
+          a.reward[(size_t)j * (size_t)a.reward_stride + env] = pn / pd;
+        }
+      }
     }
     fence_proxy_async_smem();  // my generic-proxy writes -> visible to the bulk engine
     __syncwarp();
     if (lane0) mbar_arrive(ofull0 + 8 * o);          // non-blocking hand-off to the producer
 
-    if (want_reward) {
+    if (every && a.tpe > 32) {                       // the last step's reward row
+      consumer_sync(NC);
+      if (active && row_first) reward_finish(n_inner - 1);
+    }
+    if (want_reward && !every) {
       // per-road sum(rho v)/sum(rho) in a fixed order
       const unsigned full = 0xffffffffu;
       if (a.tpe <= 32) {

@@ -192,6 +192,8 @@ template <typename T, int U> struct PipeSmem {
   // a slow one still reads tile i's
   T xS[2][XCH], xD[2][XCH], xR[2][XCH];
   T s_num[PIPE_BLOCK / 32], s_den[PIPE_BLOCK / 32];
+  // step_fused_kernel, per-step rewards: per-warp sums of the previous and the current step
+  T r_num[2][PIPE_BLOCK / 32], r_den[2][PIPE_BLOCK / 32];
   alignas(8) uint64_t full[STAGES];         // producer -> consumers: tile landed
   uint64_t empty[STAGES];                   // consumers -> producer: stage read
   uint64_t out_full[PIPE_OUT];              // consumers -> producer: result staged
@@ -237,6 +239,8 @@ template <typename T> struct PipeArgs {
   int l2_ahead;  // tiles prefetched into L2 beyond the shared-memory ring
   int n_inner;   // model steps per tile visit (step_fused_kernel, mt_fused.cuh)
   long long action_stride;  // elements between consecutive steps' actions
+  long long reward_stride;  // step_fused_kernel: > 0: a reward row per inner step, this far apart;
+                            // 0: the last step's rewards only
   BcArgs<T> bc;
   T step;
   UniformC<T> u;  // used by the UNIFORM instantiations

@@ -501,7 +501,7 @@ int launch_seg_fast(const SegArgs<T>& sa, int grid, bool fast, bool uniform, int
 template <typename T>
 int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs_out_,
                void* reward_out_, long long env0, long long n_env, cudaStream_t stream,
-               int n_inner = 1, long long action_stride = -1) {
+               int n_inner = 1, long long action_stride = -1, long long reward_stride = 0) {
   constexpr int V = Vec<T>::N;
   const mt_params& p = e->params;
   const long long B = n_env;
@@ -553,6 +553,7 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
     pa.l2_ahead = pipe_l2_ahead();
     pa.n_inner = n_inner;
     pa.action_stride = action_stride >= 0 ? action_stride : e->cfg.n_envs;
+    pa.reward_stride = reward_stride;
     pa.tpe = pa.nthr <= 32 ? next_pow2(pa.nthr) : ((pa.nthr + 31) / 32) * 32;
     pa.epc = pa.nc / pa.tpe;
     if (pa.epc > PIPE_MAX_EPC) pa.epc = PIPE_MAX_EPC;
@@ -702,12 +703,12 @@ bool can_fuse_steps(const mt_engine* e, const void* obs_in, const void* obs_out)
 
 int step_range(mt_engine* e, const void* obs_in, const void* action, void* obs_out,
                void* reward_out, long long env0, long long n_env, cudaStream_t stream,
-               int n_inner = 1, long long action_stride = -1) {
+               int n_inner = 1, long long action_stride = -1, long long reward_stride = 0) {
   if (e->cfg.dtype == MT_F64)
     return step_typed<double>(e, obs_in, action, obs_out, reward_out, env0, n_env, stream, n_inner,
-                              action_stride);
+                              action_stride, reward_stride);
   return step_typed<float>(e, obs_in, action, obs_out, reward_out, env0, n_env, stream, n_inner,
-                           action_stride);
+                           action_stride, reward_stride);
 }
 
 int step_any(mt_engine* e, const void* obs_in, const void* action, void* obs_out,
@@ -880,7 +881,7 @@ int mt_rollout(mt_engine* e, void* obs_a, void* obs_b, const void* actions, void
   if (n_steps < 0) return fail(MT_EINVAL, "mt_rollout: n_steps must be >= 0");
   CUDA_TRY(cudaSetDevice(e->cfg.device));
   const size_t stride = (size_t)e->cfg.n_envs * e->elt;
-  if (n_steps >= 2 && !rewards && can_fuse_steps(e, obs_a, obs_b)) {
+  if (n_steps >= 2 && can_fuse_steps(e, obs_a, obs_b)) {
     // one launch: every tile is read once, stepped n_steps times on chip
     // (per-step actions are read as they are needed) and written once
     if (e->params_pending) {
@@ -888,8 +889,9 @@ int mt_rollout(mt_engine* e, void* obs_a, void* obs_b, const void* actions, void
         CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, e->params_ready, 0));
       e->params_pending = false;
     }
-    const int rc = step_range(e, obs_a, actions, obs_b, nullptr, 0, e->cfg.n_envs,
-                              (cudaStream_t)stream, n_steps);
+    // (a reward row per step, when asked for, is reduced in the same launch)
+    const int rc = step_range(e, obs_a, actions, obs_b, rewards, 0, e->cfg.n_envs,
+                              (cudaStream_t)stream, n_steps, -1, rewards ? e->cfg.n_envs : 0);
     if (rc != MT_OK) return rc;
     if (result_in_b) *result_in_b = 1;
     return MT_OK;

@@ -1129,6 +1129,49 @@ def test_fused_rollout_equals_step_by_step(kind, dtype, n, b, bci, monkeypatch):
         assert np.array_equal(results[2].cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("kind", ["lwr", "arz"])
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("n,b", [(1000, 300), (64, 517), (8, 100), (256, 33)])
+def test_fused_rollout_with_per_step_rewards(kind, dtype, n, b, monkeypatch):
+    """mt_rollout with a reward row per step stays one launch: states equal the
+    step-by-step run bit for bit, every step's rewards agree with it (the sums
+    are formed in a different but fixed order) and, in f64, with the oracle."""
+    _need_gpu()
+    from mbrl_traffic_b200.engine import Engine
+    steps = 6
+    obs = make_obs(b, n, seed=n + 7, dtype=np.dtype(dtype))
+    tdt = torch.float64 if dtype == "float64" else torch.float32
+    acts = torch.as_tensor(np.random.default_rng(5).uniform(10, 30, (steps, b)),
+                           device="cuda:0").to(tdt)
+    states, rewards = [], []
+    for no_fuse in ("1", "0"):
+        monkeypatch.setenv("MT_NO_FUSE", no_fuse)
+        eng = Engine(kind, dtype, b, n)
+        eng.set_params(dx=50, dt=0.5, rho_max=1, v_max=30, lam=1,
+                       boundary_conditions="loop", tau=9)
+        a = gpu(obs).clone()
+        rew = torch.full((steps, b), float("nan"), dtype=tdt, device="cuda:0")
+        before = eng.launch_count
+        res = eng.rollout(a, torch.empty_like(a), steps, actions=acts, rewards=rew)
+        launches = eng.launch_count - before
+        assert launches == (steps if no_fuse == "1" else 1)
+        states.append(res.clone())
+        rewards.append(rew.clone())
+        eng.close()
+    torch.cuda.synchronize()
+    assert torch.equal(states[0], states[1])
+    tol = 1e-12 if dtype == "float64" else 2e-6
+    torch.testing.assert_close(rewards[1], rewards[0], rtol=tol, atol=0)
+    if dtype == "float64":
+        ref = obs
+        fn = o.arz_step if kind == "arz" else o.lwr_step
+        for k in range(steps):
+            ref = fn(ref, v_max=acts[k].cpu().numpy())
+            np.testing.assert_allclose(rewards[1][k].cpu().numpy(),
+                                       o.mean_speed_reward(ref), rtol=1e-12)
+        assert np.array_equal(states[1].cpu().numpy(), ref)
+
+
 def test_fused_host_run_with_final_reward():
     _need_gpu()
     from mbrl_traffic_b200.engine import Engine
