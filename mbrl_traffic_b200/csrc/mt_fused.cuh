@@ -186,12 +186,23 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_fused_ker
     // the exchange barrier of step j + 1 (or after the loop), so the per-step
     // reduction costs no barrier of its own
     const bool every = want_reward && a.reward_stride > 0;
+    // Runs in the warp holding the road's first thread, on all of its lanes
+    // (the sums are shared-memory broadcasts): straight-line code that the
+    // scheduler can interleave with the step's own arithmetic, instead of one
+    // lane walking through a divergent branch while the CTA waits for its warp.
     auto reward_finish = [&](int j) {
       const int w0 = t >> 5, nw = a.tpe >> 5;   // (roads wider than a warp only)
       T n = sm.r_num[j & 1][w0], d = sm.r_den[j & 1][w0];
       for (int w = 1; w < nw; ++w) { n += sm.r_num[j & 1][w0 + w]; d += sm.r_den[j & 1][w0 + w]; }
-      a.reward[(size_t)j * (size_t)a.reward_stride + env] = n / d;
+      using AX = Ar<T, false>;
+      T q = AX::div_unchecked(n, d);
+      if (!AX::div_quick(n, d)) q = n / d;      // operands outside the inline expansion's range
+      if (active && row_first) a.reward[(size_t)j * (size_t)a.reward_stride + env] = q;
     };
+    // this step's speed limit is fetched one step ahead: its L2 latency then
+    // overlaps a whole step instead of stalling the start of pass 1
+    T act_next = T(0);
+    if (active && a.action != nullptr) act_next = __ldg(a.action + env);
     // n_inner model steps on this tile; between them the state lives in
     // registers and only the edge values cross threads
     for (int j = 0; j < n_inner; ++j) {
@@ -202,7 +213,8 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_fused_ker
       xpar ^= 1;
       if (active) {
         if (a.action != nullptr) {   // this step's speed limit for my road
-          e.v_max = __ldg(a.action + (size_t)j * a.action_stride + env);
+          e.v_max = act_next;
+          if (j + 1 < n_inner) act_next = __ldg(a.action + (size_t)(j + 1) * a.action_stride + env);
           if (ARZ) e.qc = A::mul(e.rho_crit, A::mul(e.v_max, e.g_crit));
         }
         with_lam<LAMK>(e.flags, [&](auto kind) {
@@ -230,7 +242,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_fused_ker
       consumer_sync(NC);                               // exchange visible
       if (j == 0 && lane0) mbar_arrive(empty0 + 8 * s);  // stage s fully read: release it
       if (last) mbar_wait(ofree0 + 8 * o, ph_out ^ 1);   // output stage drained by its last store
-      if (every && a.tpe > 32 && j > 0 && active && row_first) reward_finish(j - 1);
+      if (every && a.tpe > 32 && j > 0 && pos < 32) reward_finish(j - 1);
 
       if (active) {
         const T S_right = xS[xi + 1], D_left = xD[xi], r_left = xR[xi];
@@ -294,7 +306,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_fused_ker
 
     if (every && a.tpe > 32) {                       // the last step's reward row
       consumer_sync(NC);
-      if (active && row_first) reward_finish(n_inner - 1);
+      if (pos < 32) reward_finish(n_inner - 1);
     }
     if (want_reward && !every) {
       // per-road sum(rho v)/sum(rho) in a fixed order
