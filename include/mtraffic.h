@@ -145,7 +145,9 @@ int mt_step(mt_engine *e, const void *obs_in, const void *action,
 /* n_steps chained steps ping-ponging between two caller-owned DEVICE batches,
  * starting from obs_a.  actions: DEVICE [n_steps, B] or NULL.  rewards:
  * DEVICE [n_steps, B] or NULL.  *result_in_b is set to 1 when the final state
- * is in obs_b, else 0. */
+ * is in obs_b, else 0; the other batch is scratch.  Batches whose roads fit
+ * one tile run as ONE launch (state in registers between steps, one HBM read
+ * and write per road); results are bit-identical to n_steps mt_step calls. */
 int mt_rollout(mt_engine *e, void *obs_a, void *obs_b, const void *actions,
                void *rewards, int32_t n_steps, void *stream,
                int32_t *result_in_b);
