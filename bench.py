@@ -268,6 +268,24 @@ def run_ours(args, rank, local_rank, world):
     sus_clocks = sus_sampler.stop()
     sus_steps = sus_reps * gk
 
+    # independent batches: the timed launches DO read batches that the previous
+    # launch did not write, which MT_FLAG_INDEPENDENT_INPUT lets the engine use
+    # (the next launch fetches its input while the previous one drains).  Not
+    # the headline: a rollout's input is the previous step's output.
+    eng.set_params(independent_input=True, **PARAMS)
+    with torch.cuda.stream(stream):
+        launch_streaming(N_SETS)
+    torch.cuda.synchronize()
+    ind_graph = capture(lambda k: launch_streaming(k), gk)
+    ind_graph.replay()
+    ind_reps = max(1, min(K, 2000) // gk)
+    ind_s = timed([(ind_graph, ind_reps)])
+    ind_steps = ind_reps * gk
+    eng.set_params(**PARAMS)
+    with torch.cuda.stream(stream):
+        launch_streaming(1)                       # (consumes the parameter-ready event
+    torch.cuda.synchronize()                      #  outside of any graph capture)
+
     # chained: one batch ping-ponged in place
     chain_plan = [(capture(launch_chained, gk + (gk & 1)), max(1, full))]
     chain_plan[0][0].replay()
@@ -296,9 +314,10 @@ def run_ours(args, rank, local_rank, world):
     obs_bytes = N_ENVS * 2 * N_CELLS * 8
 
     if world > 1:
-        t = torch.tensor([seconds, chain_s, e2e_s, sus_s], dtype=torch.float64, device=dev)
+        t = torch.tensor([seconds, chain_s, e2e_s, sus_s, ind_s], dtype=torch.float64,
+                         device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        seconds, chain_s, e2e_s, sus_s = [float(x) for x in t.tolist()]
+        seconds, chain_s, e2e_s, sus_s, ind_s = [float(x) for x in t.tolist()]
 
     cells = N_ENVS * N_CELLS
     value = world * cells * K / seconds
@@ -332,6 +351,13 @@ def run_ours(args, rank, local_rank, world):
                       "steps": sus_steps, "ms_per_step": sus_s / sus_steps * 1e3,
                       "roofline_frac": cells * BYTES_PER_CELL_UPDATE / (sus_s / sus_steps) / 1e9 / peak,
                       "clocks": sus_clocks},
+        "independent_batches": {
+            "value": world * cells * ind_steps / ind_s, "unit": "cell-updates/s",
+            "ms_per_step": ind_s / ind_steps * 1e3,
+            "roofline_frac": cells * BYTES_PER_CELL_UPDATE / (ind_s / ind_steps) / 1e9 / peak,
+            "note": "same launches with MT_FLAG_INDEPENDENT_INPUT: a step's loads start "
+                    "while the previous launch drains (valid because consecutive timed "
+                    "steps work on different batches; not valid for chained steps)"},
         "chained": {"value": world * cells * chain_steps / chain_s,
                     "unit": "cell-updates/s",
                     "note": "one batch ping-ponged in place (rollout pattern; "

@@ -85,9 +85,18 @@ enum {
   MT_FLAG_FAST_MATH = 1,  /* allow FMA contraction, approximate division and
                              x**lam as exp(lam log x) for a general lam
                              (not bit-comparable; throughput mode)         */
-  MT_FLAG_NO_PIPELINE = 2 /* use the direct (one CTA per road tile) kernel
+  MT_FLAG_NO_PIPELINE = 2,/* use the direct (one CTA per road tile) kernel
                              instead of the persistent TMA-pipelined one;
                              same results, for A/B measurements and tests  */
+  MT_FLAG_INDEPENDENT_INPUT = 4
+                          /* the caller guarantees that the INPUT batch of a
+                             step is not written by the work enqueued right
+                             before it on the stream (independent batches, a
+                             pool of buffers).  The step kernel then starts
+                             fetching its input while the previous launch
+                             still drains; its stores still wait for it.
+                             Same results.  Do NOT set it for chained steps
+                             (input = the previous step's output).          */
 };
 
 /* Fixed for the life of an engine. */

@@ -248,6 +248,11 @@ template <typename T> struct PipeArgs {
   // each CTA's first ring-full, sched[1] counts finished CTAs (the last one
   // re-arms both).  nullptr: static round-robin schedule.
   unsigned int* sched = nullptr;
+  // The input batch was not written by the launch this one programmatically
+  // depends on: the first ring-full of loads is issued BEFORE waiting for that
+  // launch to finish (only the stores wait), so this launch's pipeline fills
+  // while the previous one drains.  See MT_FLAG_INDEPENDENT_INPUT.
+  int early_loads = 0;
 };
 
 // Which instantiations of step_pipe_kernel draw their tiles from a counter.
@@ -315,7 +320,9 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
     fence_mbar_init();
   }
   __syncthreads();
-  pdl_wait_prior_grid();  // everything above overlapped the previous kernel's tail
+  // everything above overlapped the previous kernel's tail
+  const bool early = a.early_loads != 0;
+  if (!early) pdl_wait_prior_grid();
 
   // ======================= producer warp ===================================
   if (t >= NC) {
@@ -361,6 +368,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
         for (int i = 0; i < pre; ++i) issue_load(i);
         const int ahead = a.l2_ahead;
         for (int i = PIPE_STAGES; i < PIPE_STAGES + ahead && i < n_my; ++i) prefetch(i);
+        if (early) pdl_wait_prior_grid();   // before the first store
         for (int i = 0; i < n_my; ++i) {
           const int tile = (int)blockIdx.x + i * (int)gridDim.x;
           const int s = i % PIPE_STAGES, o = i % PIPE_OUT;
@@ -430,6 +438,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
         };
         MT_STAMP(1);
         for (int s = 0; s < PIPE_STAGES; ++s) issue_load(s, grab());
+        if (early) pdl_wait_prior_grid();   // before the first store and the first counter draw
         // tiles drawn and prefetched into L2 but not yet loaded: a ring in
         // shared memory (this thread only), oldest at index i % PIPE_QMAX
         const int ahead = a.l2_ahead < PIPE_QMAX ? a.l2_ahead : PIPE_QMAX;

@@ -574,6 +574,10 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
         if (e->hs[j] != nullptr && stream == e->hs[j]) slot = j + 1;
       pa.sched = e->sched + 2 * slot;
     }
+    // consumers of the early-load variant must not touch global memory before
+    // the previous launch is done: scalar parameters, no speed limits, no rewards
+    pa.early_loads = ((p.flags & MT_FLAG_INDEPENDENT_INPUT) && e->uniform && action == nullptr &&
+                      reward_out == nullptr && n_inner == 1 && pipe_use_pdl()) ? 1 : 0;
     int rc;
     if (e->cfg.model == MT_MODEL_ARZ)
       rc = U == 2 ? launch_pipe_model<T, 1, 2>(pa, grid, fast, e->uniform, e->lamk, stream)

@@ -245,6 +245,49 @@ def test_dynamic_tile_schedule_with_action_reward_and_table():
     eng.close()
 
 
+@pytest.mark.parametrize("kind,dtype,b", [("arz", "float64", 1500), ("lwr", "float64", 5000),
+                                          ("arz", "float32", 1500)])
+def test_independent_input_flag_same_results(kind, dtype, b):
+    """MT_FLAG_INDEPENDENT_INPUT (loads issued before the previous launch has
+    finished, stores after): over a pool of independent batches, launched back
+    to back from a CUDA graph, every output equals the default mode's; with
+    rewards requested the flag is ignored."""
+    _need_gpu()
+    from mbrl_traffic_b200.engine import Engine
+    n, sets, steps = 1000, 3, 12
+    tdt = torch.float64 if dtype == "float64" else torch.float32
+    ins = [gpu(make_obs(b, n, seed=60 + j)).to(tdt) for j in range(sets)]
+    res = {}
+    for flag in (False, True):
+        eng = Engine(kind, dtype, b, n)
+        eng.set_params(dx=50, dt=0.5, rho_max=1, v_max=30, lam=1, tau=9,
+                       boundary_conditions="loop", fast_math=(dtype == "float32"),
+                       independent_input=flag)
+        outs = [torch.zeros_like(x) for x in ins]
+        rew = torch.empty(b, dtype=tdt, device="cuda:0")
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            for k in range(sets):
+                eng.step(ins[k], outs[k], stream=s)
+            s.synchronize()
+            for t_ in outs:
+                t_.zero_()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                for k in range(steps):
+                    eng.step(ins[k % sets], outs[k % sets], stream=s)
+            for _ in range(3):
+                g.replay()
+            eng.step(ins[0], outs[0], reward=rew, stream=s)
+            s.synchronize()
+        res[flag] = [t_.clone() for t_ in outs] + [rew.clone()]
+        eng.close()
+    for x, y in zip(res[False], res[True]):
+        assert torch.equal(x, y)
+    if dtype == "float64":
+        assert np.array_equal(res[True][1].cpu().numpy(), oracle_step(kind, ins[1].cpu().numpy()))
+
+
 def test_dynamic_tile_schedule_f32_fast():
     _need_gpu()
     obs32 = make_obs(4800, 1000, seed=21, dtype=np.float32)

@@ -37,6 +37,8 @@ def main():
     ap.add_argument("--per-env", action="store_true",
                     help="pass the parameters as per-road device arrays")
     ap.add_argument("--rho-max", type=float, default=1.0)
+    ap.add_argument("--independent", action="store_true",
+                    help="MT_FLAG_INDEPENDENT_INPUT (valid for the streaming measurement only)")
     ap.add_argument("--lam", type=float, default=1.0)
     ap.add_argument("--bc", default="loop",
                     help="loop | extend_both | inflow_outflow (constant 0.3 rho_max inflow, "
@@ -64,11 +66,13 @@ def main():
             return lo + (hi - lo) * torch.rand(b, generator=g, dtype=tdt, device="cuda")
         eng.set_params(dx=50, dt=0.5, rho_max=rnd(0.9, 1.5) * args.rho_max, v_max=rnd(20, 40),
                        lam=rnd(0.5, 3.0), boundary_conditions=bc, tau=rnd(5, 25),
-                       fast_math=args.fast, no_pipeline=args.direct, gamma=gamma)
+                       fast_math=args.fast, no_pipeline=args.direct, gamma=gamma,
+                       independent_input=args.independent)
     else:
         eng.set_params(dx=50, dt=0.5, rho_max=par(args.rho_max), v_max=par(30),
                        lam=par(args.lam), boundary_conditions=bc, tau=par(9),
-                       fast_math=args.fast, no_pipeline=args.direct, gamma=gamma)
+                       fast_math=args.fast, no_pipeline=args.direct, gamma=gamma,
+                       independent_input=args.independent)
     rng = np.random.default_rng(0)
     rho = args.rho_max * rng.uniform(0.05, 0.9, (b, n))
     v = 30 * (1 - rho / args.rho_max) + rng.normal(0, 1, (b, n))
