@@ -127,10 +127,17 @@ def time_cpu_port(steps, warmup, min_seconds=3.0):
     """Times oracle/c_oracle.c (OpenMP, all host threads) on the full
     workload shape; a bounded number of steps."""
     from oracle import c_oracle
-    threads = c_oracle.max_threads()
+    # all the host threads this process may use -- torchrun exports
+    # OMP_NUM_THREADS=1 to its workers, which would silently make this a
+    # one-core baseline
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
+    threads = max(threads, c_oracle.max_threads())
     obs = make_obs(0)
     out = np.empty_like(obs)
-    kw = dict(PARAMS)
+    kw = dict(PARAMS, n_threads=threads)
     for _ in range(max(1, warmup)):
         c_oracle.step("arz", obs, out=out, **kw)
         obs, out = out, obs
