@@ -96,7 +96,11 @@ enum {
                              fetching its input while the previous launch
                              still drains; its stores still wait for it.
                              Same results.  Do NOT set it for chained steps
-                             (input = the previous step's output).          */
+                             (input = the previous step's output).  Used only
+                             when this launch and the engine's previous one
+                             on the stream both fill the GPU (anything older
+                             is then known to have finished), with scalar
+                             parameters and without speed limits / rewards. */
 };
 
 /* Fixed for the life of an engine. */

@@ -142,6 +142,10 @@ struct mt_engine {
   // tile-schedule counters of the pipelined kernel: one {next, done} pair per
   // stream the engine launches on (slot 0: the caller's stream; 1..: hs[])
   unsigned int* sched = nullptr;
+  // MT_FLAG_INDEPENDENT_INPUT bookkeeping: stream of the previous launch when
+  // it was a pipelined step that filled every CTA slot of the GPU, else null
+  cudaStream_t last_full_pipe_stream = nullptr;
+  bool last_full_pipe = false;
   int max_tiles = 1;
   int sm_count = 148;
   bool have_params = false;
@@ -502,6 +506,9 @@ template <typename T>
 int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs_out_,
                void* reward_out_, long long env0, long long n_env, cudaStream_t stream,
                int n_inner = 1, long long action_stride = -1, long long reward_stride = 0) {
+  // (see the early-load bookkeeping in the pipelined branch)
+  const bool prev_full_pipe = e->last_full_pipe;
+  e->last_full_pipe = false;
   constexpr int V = Vec<T>::N;
   const mt_params& p = e->params;
   const long long B = n_env;
@@ -574,10 +581,21 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
         if (e->hs[j] != nullptr && stream == e->hs[j]) slot = j + 1;
       pa.sched = e->sched + 2 * slot;
     }
-    // consumers of the early-load variant must not touch global memory before
-    // the previous launch is done: scalar parameters, no speed limits, no rewards
+    // Early loads (MT_FLAG_INDEPENDENT_INPUT).  The caller vouches for the launch
+    // right before this one; older launches must be finished on their own
+    // account, which holds when that launch AND this one fill every CTA slot: a
+    // CTA of this launch then only finds room once a CTA of the previous launch
+    // has exited, i.e. after the previous launch has itself waited for
+    // everything before it.  Consumers must not touch global memory before the
+    // wait: scalar parameters, no speed limits, no rewards.
+    const bool full_grid = (long long)grid == slots;
     pa.early_loads = ((p.flags & MT_FLAG_INDEPENDENT_INPUT) && e->uniform && action == nullptr &&
-                      reward_out == nullptr && n_inner == 1 && pipe_use_pdl()) ? 1 : 0;
+                      reward_out == nullptr && n_inner == 1 && pipe_use_pdl() && full_grid &&
+                      prev_full_pipe && e->last_full_pipe_stream == stream) ? 1 : 0;
+    e->last_full_pipe = full_grid && n_inner == 1 &&
+                        !pipe_use_ring(sizeof(T) == 4, fast, e->cfg.model == MT_MODEL_ARZ,
+                                       pa.sched != nullptr);
+    e->last_full_pipe_stream = stream;
     int rc;
     if (e->cfg.model == MT_MODEL_ARZ)
       rc = U == 2 ? launch_pipe_model<T, 1, 2>(pa, grid, fast, e->uniform, e->lamk, stream)
@@ -850,6 +868,7 @@ int mt_set_params(mt_engine* e, const mt_params* p, void* stream) {
                        (const float*)p->rho_crit_env};
     set_params_kernel<float><<<grid, block, 0, s>>>(a);
   }
+  e->last_full_pipe = false;
   e->launches++;
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(e->params_ready, s));
