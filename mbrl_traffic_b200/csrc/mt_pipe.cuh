@@ -253,6 +253,7 @@ template <typename T> struct PipeArgs {
   // launch to finish (only the stores wait), so this launch's pipeline fills
   // while the previous one drains.  See MT_FLAG_INDEPENDENT_INPUT.
   int early_loads = 0;
+  int early_l2 = 2;  // tiles per CTA pulled towards L2 before the grid-dependency wait
 };
 
 // Which instantiations of step_pipe_kernel draw their tiles from a counter.
@@ -322,6 +323,28 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
   __syncthreads();
   // everything above overlapped the previous kernel's tail
   const bool early = a.early_loads != 0;
+#ifndef MT_NO_EARLY_L2
+  if (!early && t == NC) {
+    // The loads themselves must wait for the previous launch (its output may be
+    // this launch's input), but an L2 prefetch is not a read: it returns no
+    // data, and L2 is the point of coherence, so lines the previous launch
+    // still writes are simply updated in place.  The CTA's first tiles are
+    // therefore pulled towards L2 while the previous launch drains (two tiles
+    // measured best: more competes with that launch's own tail).
+    const unsigned char* gin0 = reinterpret_cast<const unsigned char*>(a.in);
+    for (int i = 0; i < a.early_l2; ++i) {
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      if (tile >= a.n_tiles) break;
+      const int envs = tile == last_tile ? last_envs : a.epc;
+      if (ARZ) {
+        bulk_prefetch_l2(gin0 + (size_t)tile * tile_bytes, (uint32_t)envs * row_bytes);
+      } else {
+        for (int r = 0; r < envs; ++r)
+          bulk_prefetch_l2(gin0 + (size_t)tile * tile_bytes + (size_t)r * row_bytes, row_bytes >> 1);
+      }
+    }
+  }
+#endif
   if (!early) pdl_wait_prior_grid();
 
   // ======================= producer warp ===================================

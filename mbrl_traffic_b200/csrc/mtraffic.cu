@@ -558,6 +558,11 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
     pa.nthr = N / (U * V);
     pa.nc = PIPE_BLOCK / U;
     pa.l2_ahead = pipe_l2_ahead();
+    {
+      static int early_l2 = -1;   // MT_PIPE_EARLY_L2: A/B knob; 2 measured best (0..14 tried)
+      if (early_l2 < 0) { const char* s = getenv("MT_PIPE_EARLY_L2"); early_l2 = s ? atoi(s) : 2; }
+      pa.early_l2 = early_l2;
+    }
     pa.n_inner = n_inner;
     pa.action_stride = action_stride >= 0 ? action_stride : e->cfg.n_envs;
     pa.reward_stride = reward_stride;
