@@ -110,6 +110,10 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U, 2) step_ring_kernel(const Pipe
     fence_mbar_init();
   }
   __syncthreads();
+  // towards L2 before waiting for the previous launch (see step_pipe_kernel:
+  // a prefetch returns no data, so this is safe for dependent launches too)
+  if (t == 0)
+    for (int i = 0; i < a.early_l2 && i < n_my; ++i) prefetch(i);
   pdl_wait_prior_grid();  // everything above overlapped the previous kernel's tail
 
   const int ahead = a.l2_ahead;
