@@ -171,7 +171,8 @@ class KShootPolicy(object):
         if actions is None:
             actions = self.sample_actions()
         k = self.num_particles
-        self._a.copy_(obs.repeat_interleave(k, dim=0))
+        # every road's state to its k particles: one broadcasting copy
+        self._a.view(self.n_envs, k, -1).copy_(obs[:, None, :].expand(-1, k, -1))
         self.engine.rollout(self._a, self._b, self.traj_length,
                             actions=actions.contiguous(), rewards=self._rew)
         returns = self._rew.sum(dim=0).view(self.n_envs, k)
