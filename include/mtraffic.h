@@ -177,6 +177,12 @@ int mt_step_host(mt_engine *e, const void *obs_in_host,
 int mt_density_sqerr(mt_engine *e, const void *obs_pred,
                      const void *obs_target, void *out_per_env, void *stream);
 
+/* flags_out[b] = 1 if any density or speed of road b is inf or NaN, else 0
+ * (DEVICE int32 [B]).  The reference has no such check: a diverged road just
+ * propagates NaN through get_next_obs (arz.py:205-221); rollout loops use this
+ * to reset or drop roads an erratic controller has driven unstable. */
+int mt_nonfinite(mt_engine *e, const void *obs, int32_t *flags_out, void *stream);
+
 /* Microscopic -> macroscopic aggregation (the reference's notebook loop,
  * experiments/plotting_results.ipynb cell 8): records (time, position, speed)
  * -> per (time row, section) mean speed and density.  All pointers are DEVICE

@@ -24,7 +24,7 @@ EXPORTS = (
     "mt_version", "mt_last_error", "mt_create", "mt_destroy", "mt_set_params",
     "mt_step", "mt_rollout", "mt_step_host", "mt_density_sqerr",
     "mt_launch_count", "mt_alloc_pinned", "mt_free_pinned", "mt_aggregate",
-    "mt_halo_create", "mt_halo_destroy", "mt_halo_handle", "mt_halo_connect",
+    "mt_nonfinite", "mt_halo_create", "mt_halo_destroy", "mt_halo_handle", "mt_halo_connect",
     "mt_halo_connect_local", "mt_halo_push", "mt_halo_pull", "mt_halo_status",
 )
 
@@ -106,6 +106,8 @@ def load():
     lib.mt_alloc_pinned.argtypes = [ctypes.c_uint64, ctypes.POINTER(vp)]
     lib.mt_free_pinned.restype = ctypes.c_int
     lib.mt_free_pinned.argtypes = [vp]
+    lib.mt_nonfinite.restype = ctypes.c_int
+    lib.mt_nonfinite.argtypes = [vp, vp, vp, vp]
     lib.mt_halo_create.restype = ctypes.c_int
     lib.mt_halo_create.argtypes = [i32, i32, i32, ctypes.POINTER(vp)]
     lib.mt_halo_destroy.restype = None

@@ -128,6 +128,27 @@ __global__ void density_sqerr_kernel(const T* __restrict__ pred, const T* __rest
   if (lane == 0) out[env] = s;
 }
 
+// ---------------------------------------------------------------------------
+// failure detection: per-road "state is not finite" flag (a diverged road --
+// an erratic controller can drive the reference scheme itself unstable --
+// shows up as inf/NaN cells; callers reset or drop such roads)
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void nonfinite_kernel(const T* __restrict__ obs, int* __restrict__ out, long long B,
+                                 int N) {
+  const long long env = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (env >= B) return;
+  const int lane = threadIdx.x & 31;
+  const T* p = obs + env * (2LL * N);
+  int bad = 0;
+  for (int i = lane; i < 2 * N; i += 32) {
+    const T x = p[i];
+    bad |= !(x - x == T(0));   // inf - inf and NaN - NaN are NaN
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  if (lane == 0) out[env] = bad ? 1 : 0;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------
@@ -1053,6 +1074,24 @@ int mt_density_sqerr(mt_engine* e, const void* obs_pred, const void* obs_target,
   else
     density_sqerr_kernel<float><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(
         (const float*)obs_pred, (const float*)obs_target, (float*)out_per_env, B, N);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return MT_OK;
+}
+
+int mt_nonfinite(mt_engine* e, const void* obs, int32_t* flags_out, void* stream) {
+  if (!e || !obs || !flags_out) return fail(MT_EINVAL, "mt_nonfinite: NULL argument");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  const long long B = e->cfg.n_envs;
+  const int N = (int)e->cfg.n_cells, wpb = 8;
+  const unsigned grid = (unsigned)((B + wpb - 1) / wpb);
+  if (e->cfg.dtype == MT_F64)
+    nonfinite_kernel<double><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const double*)obs,
+                                                                          flags_out, B, N);
+  else
+    nonfinite_kernel<float><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const float*)obs,
+                                                                         flags_out, B, N);
+  e->last_full_pipe = false;
   e->launches++;
   CUDA_TRY(cudaGetLastError());
   return MT_OK;

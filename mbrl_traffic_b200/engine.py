@@ -193,6 +193,12 @@ class Engine(object):
             self._h, _ptr(obs_in), _ptr(action), _ptr(obs_out), _ptr(reward),
             int(n_steps)))
 
+    def nonfinite(self, obs, flags_out, stream=None):
+        """``mt_nonfinite``: ``flags_out`` (int32 ``(B,)`` device tensor) gets 1
+        for every road whose state holds an inf or a NaN."""
+        _lib.check(self._lib.mt_nonfinite(self._h, _ptr(obs), _ptr(flags_out),
+                                          _stream_ptr(stream)))
+
     def density_sqerr(self, obs_pred, obs_target, out, stream=None):
         """``mt_density_sqerr`` on device buffers."""
         _lib.check(self._lib.mt_density_sqerr(

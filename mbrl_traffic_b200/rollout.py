@@ -68,6 +68,19 @@ class BatchedMacroEnv(object):
         return self.obs, self.reward, self.t >= self.horizon, {}
 
 
+def _diverged(self):
+    """int32 ``(B,)`` device tensor: 1 for every road whose current state holds
+    an inf or a NaN (``mt_nonfinite``).  An erratic controller can drive the
+    reference scheme itself unstable; such roads are usually reset."""
+    if getattr(self, "_flags", None) is None:
+        self._flags = torch.empty(self.n_envs, dtype=torch.int32, device=self.device)
+    self.engine.nonfinite(self.obs, self._flags)
+    return self._flags
+
+
+BatchedMacroEnv.diverged = _diverged
+
+
 class FeedForwardActor(nn.Module):
     """``[2N -> 256 -> 256 -> 1]`` actor, the shape of the reference's SAC
     policy network (``policies/sac.py:303-322``, ``utils/train.py:152``); the

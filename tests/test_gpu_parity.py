@@ -288,6 +288,32 @@ def test_independent_input_flag_same_results(kind, dtype, b):
         assert np.array_equal(res[True][1].cpu().numpy(), oracle_step(kind, ins[1].cpu().numpy()))
 
 
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_nonfinite_flags(dtype):
+    _need_gpu()
+    from mbrl_traffic_b200.engine import Engine
+    b, n = 300, 1000
+    tdt = torch.float64 if dtype == "float64" else torch.float32
+    x = gpu(make_obs(b, n, seed=3)).to(tdt)
+    x[7, 5] = float("nan")
+    x[100, n + 999] = float("inf")
+    x[299, 0] = -float("inf")
+    eng = Engine("arz", dtype, b, n)
+    flags = torch.full((b,), -1, dtype=torch.int32, device="cuda:0")
+    eng.nonfinite(x, flags)
+    expect = np.zeros(b, dtype=np.int32)
+    expect[[7, 100, 299]] = 1
+    assert np.array_equal(flags.cpu().numpy(), expect)
+    eng.close()
+    if dtype == "float64":
+        from mbrl_traffic_b200.rollout import BatchedMacroEnv
+        m = make_model("arz")
+        env = BatchedMacroEnv(m, b, n, horizon=4, dtype=tdt)
+        env.reset(x)
+        assert np.array_equal(env.diverged().cpu().numpy(), expect)
+        m.close()
+
+
 def test_dynamic_tile_schedule_f32_fast():
     _need_gpu()
     obs32 = make_obs(4800, 1000, seed=21, dtype=np.float32)
