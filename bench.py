@@ -177,7 +177,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": base["value"], "unit": "cell-updates/s",
                 "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 # --------------------------------------------------------------------------- #
@@ -393,7 +393,7 @@ def run_ours(args, rank, local_rank, world):
                               "bit_equal": bool(np.array_equal(got, ref)),
                               "max_abs_diff": float(np.max(np.abs(got - ref)))}
             line["cpu_baseline"] = base
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     pin_in.free()
     pin_out.free()
     if world > 1:
@@ -401,7 +401,26 @@ def run_ours(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+_OUT_FD = None
+
+
+def emit(text):
+    """The one JSON line goes to the process's real stdout; everything else
+    written to fd 1 meanwhile -- NCCL prints its version there when
+    NCCL_DEBUG=VERSION -- was sent to stderr by main()."""
+    sys.stdout.flush()
+    data = (text + "\n").encode()
+    if _OUT_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_OUT_FD, data)
+
+
 def main():
+    global _OUT_FD
+    sys.stdout.flush()
+    _OUT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
