@@ -17,10 +17,18 @@
 //     input stage, wait(out_free[o]), finish the update and write the result
 //     to the output stage, then arrive on out_full[o] WITHOUT blocking and
 //     move on to the next tile.
+//     (The interior cells of a thread are finished BEFORE the barrier: they
+//     need nothing from other threads -- cell_mid / cell_edges in mt_cell.cuh.)
 // Loads for the next PIPE_STAGES-1 tiles and the stores of previous tiles are
 // in flight while the consumers compute, so HBM latency is decoupled from the
 // FP64 work; all hand-offs are mbarriers (no CTA-wide __syncthreads in the
 // steady state).
+//
+// Tile schedule: static round-robin, or (HBM-bound instantiations, large
+// batches) tiles drawn from a per-engine counter -- see PipeDynamic.
+// Launch boundary: programmatic dependent launch; before waiting for the
+// previous launch the producer prefetches its first tiles towards L2, and with
+// MT_FLAG_INDEPENDENT_INPUT it issues the first ring-full of loads outright.
 #pragma once
 #include <stdint.h>
 #include "mtraffic.h"
