@@ -181,3 +181,27 @@ def test_nonlocal_model_host_contract(tmp_path):
     m2.eta, m2.kernel = 100, "constant"
     m2.load(str(tmp_path / "model.json"))
     assert m2.eta == 800 and m2.kernel == "linear"
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """include/mtraffic.h compiles as C99 (no C++ in the boundary) and a C
+    program using it links against libmtraffic.so and reads its version."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    lib_dir = os.path.join(ROOT, "mbrl_traffic_b200")
+    if not os.path.isfile(os.path.join(lib_dir, "libmtraffic.so")):
+        pytest.skip("libmtraffic.so not built")
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "mtraffic.h"\n'
+                   'int main(void) { mt_config c; mt_params p; (void)c; (void)p;\n'
+                   '  printf("%d %d %d\\n", mt_version(), (int)sizeof(mt_config), MT_IPC_HANDLE_BYTES);\n'
+                   '  return 0; }\n')
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror",
+                    "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", lib_dir, "-lmtraffic", "-Wl,-rpath," + lib_dir], check=True)
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE, universal_newlines=True, check=True)
+    version, cfg_size, handle = out.stdout.split()
+    assert int(version) > 0 and int(cfg_size) == 40 and int(handle) == 64
