@@ -26,6 +26,23 @@ __device__ __forceinline__ void arz_pass1(const EnvC<T>& e, const T (&rho)[CPT],
                                           T (&y)[CPT], T (&r)[CPT], T (&D)[CPT], T (&S)[CPT]) {
   using A = Ar<T, FAST>;
   bool ok = true;
+#ifdef MT_DIV_SHORTCUT
+  // (round 2 candidate, off by default: y / rho from t = v - V(rho) and one
+  // residual instead of a division -- DESIGN.md section 9, item 1)
+  if constexpr (sizeof(T) == 8 && !FAST) {
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      T t;
+      arz_cell_nodiv_t<T, FAST, LAMK>(e, rho[k], v[k], t, y[k], D[k], S[k]);
+      r[k] = quot_of_product(t, rho[k], y[k], ok);
+    }
+    if (!ok) {  // rare: a power-of-two t, a zero density, operands out of range
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) r[k] = A::div(y[k], rho[k]);
+    }
+    return;
+  }
+#endif
 #pragma unroll
   for (int k = 0; k < CPT; ++k) {
     arz_cell_nodiv<T, FAST, LAMK>(e, rho[k], v[k], y[k], D[k], S[k]);
