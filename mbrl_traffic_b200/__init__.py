@@ -13,9 +13,11 @@ from mbrl_traffic_b200.params import LWR_MODEL_PARAMS
 from mbrl_traffic_b200.params import ARZ_MODEL_PARAMS
 from mbrl_traffic_b200.params import NONLOCAL_MODEL_PARAMS
 from mbrl_traffic_b200.engine import Engine, PinnedArray
+from mbrl_traffic_b200.optimizers import (NelderMead, CrossEntropyMethod,
+                                          GeneticAlgorithm)
 
 __all__ = [
     "Model", "LWRModel", "ARZModel", "NonLocalModel", "Engine",
-    "PinnedArray",
+    "PinnedArray", "NelderMead", "CrossEntropyMethod", "GeneticAlgorithm",
     "LWR_MODEL_PARAMS", "ARZ_MODEL_PARAMS", "NONLOCAL_MODEL_PARAMS",
 ]

@@ -41,6 +41,7 @@ class FiniteVolumeModel(Model):
         self.fast_math = fast_math
         self._engines = {}
         self._param_keys = {}
+        self._pop_cache = {}
 
     # ------------------------------------------------------------------ #
     # reference-compatible no-ops                                        #
@@ -166,11 +167,24 @@ class FiniteVolumeModel(Model):
         out = torch.empty_like(batch)
         if action is not None:
             action = action.to(batch.dtype).reshape(n_envs).contiguous()
+        if reward_out is not None and reward_out.numel() != n_envs:
+            raise ValueError("reward_out must hold one value per road (the "
+                             "final step's reward), as on the host path")
         if n_steps == 1:
             eng.step(batch, out, action=action, reward=reward_out)
         else:
+            # the same speed limits apply to every step (as on the host path);
+            # reward_out receives the final step's rewards: that step is issued
+            # on its own, the steps before it as one fused launch
             work = batch.clone()
-            res = eng.rollout(work, out, n_steps, rewards=reward_out)
+            fused = n_steps if reward_out is None else n_steps - 1
+            acts = None if action is None else \
+                action[None, :].expand(fused, n_envs).contiguous()
+            res = eng.rollout(work, out, fused, actions=acts)
+            if reward_out is not None:
+                other = out if res is work else work
+                eng.step(res, other, action=action, reward=reward_out)
+                res = other
             out = res
         return out[0] if squeeze else out
 
@@ -230,30 +244,39 @@ class FiniteVolumeModel(Model):
                          dtype=arr.dtype)
         p, b, n = cand.shape[0], arr.shape[0], arr.shape[1] // 2
         tdt = torch.float64 if arr.dtype == np.float64 else torch.float32
-        s = torch.as_tensor(np.ascontiguousarray(arr), device=dev).repeat(p, 1)
-        t = torch.as_tensor(np.ascontiguousarray(tgt), device=dev).repeat(p, 1)
-        eng = Engine(self._engine_model, arr.dtype.name, p * b, n, device=self.device,
-                     max_n_eta=self._max_n_eta())
-        try:
-            kw = dict(dx=self.dx, dt=self.dt,
-                      boundary_conditions=self.boundary_conditions)
-            for name in self._param_names:
-                kw[name] = getattr(self, name)
-            kw.update(self._engine_kwargs())
-            for j, name in enumerate(self._fit_names):
-                kw[name] = torch.as_tensor(cand[:, j], device=dev).to(tdt) \
-                    .repeat_interleave(b).contiguous()
-            if "gamma" in kw and isinstance(kw["gamma"], np.ndarray):
-                kw["gamma"] = torch.as_tensor(kw["gamma"], device=dev).to(tdt)
-            eng.set_params(fast_math=self.fast_math, **kw)
-            pred = torch.empty_like(s)
-            eng.step(s, pred)
-            sq = torch.empty(p * b, dtype=tdt, device=dev)
-            eng.density_sqerr(pred, t, sq)
-            out = (sq.view(p, b).sum(dim=1) / (b * n)).double().cpu().numpy()
-        finally:
-            eng.close()
-        return out
+        # one engine and one set of device buffers per population shape, kept
+        # across generations (an optimizer calls this once per generation)
+        key = (p, b, n, arr.dtype.name, self.device)
+        ws = self._pop_cache.get(key)
+        if ws is None:
+            eng = Engine(self._engine_model, arr.dtype.name, p * b, n, device=self.device,
+                         max_n_eta=self._max_n_eta())
+            ws = dict(eng=eng,
+                      s=torch.empty(p * b, 2 * n, dtype=tdt, device=dev),
+                      t=torch.empty(p * b, 2 * n, dtype=tdt, device=dev),
+                      pred=torch.empty(p * b, 2 * n, dtype=tdt, device=dev),
+                      sq=torch.empty(p * b, dtype=tdt, device=dev))
+            self._pop_cache[key] = ws
+        eng = ws["eng"]
+        # every candidate gets its own copy of the rows: one broadcasting copy
+        ws["s"].view(p, b, 2 * n).copy_(
+            torch.as_tensor(np.ascontiguousarray(arr), device=dev)[None])
+        ws["t"].view(p, b, 2 * n).copy_(
+            torch.as_tensor(np.ascontiguousarray(tgt), device=dev)[None])
+        kw = dict(dx=self.dx, dt=self.dt,
+                  boundary_conditions=self.boundary_conditions)
+        for name in self._param_names:
+            kw[name] = getattr(self, name)
+        kw.update(self._engine_kwargs())
+        for j, name in enumerate(self._fit_names):
+            kw[name] = torch.as_tensor(cand[:, j], device=dev).to(tdt) \
+                .repeat_interleave(b).contiguous()
+        if "gamma" in kw and isinstance(kw["gamma"], np.ndarray):
+            kw["gamma"] = torch.as_tensor(kw["gamma"], device=dev).to(tdt)
+        eng.set_params(fast_math=self.fast_math, **kw)
+        eng.step(ws["s"], ws["pred"])
+        eng.density_sqerr(ws["pred"], ws["t"], ws["sq"])
+        return (ws["sq"].view(p, b).sum(dim=1) / (b * n)).double().cpu().numpy()
 
     def _make_optimizer(self, optimizer_cls, param_low, param_high, fitness_fn):
         """Build the optimizer the way the reference does (lwr.py:180-186);
@@ -274,5 +297,8 @@ class FiniteVolumeModel(Model):
         """Release the engines (device memory)."""
         for eng in self._engines.values():
             eng.close()
+        for ws in self._pop_cache.values():
+            ws["eng"].close()
         self._engines = {}
         self._param_keys = {}
+        self._pop_cache = {}

@@ -15,7 +15,8 @@ class ARZModel(FiniteVolumeModel):
     ``model.json`` schema are the reference's (arz.py:60-145, 205-221,
     526-558).  The step -- relative flow ``y = rho (v - V(rho))``, supply/demand
     flux, semi-implicit relaxation and the three boundary modes
-    (arz.py:223-467) -- runs in ``arz_step_vec_kernel``; the relaxation's
+    (arz.py:223-467) -- runs in ``mt::step_pipe_kernel<T, 1, ...>``
+    (csrc/mt_pipe.cuh; per-cell arithmetic in csrc/mt_cell.cuh ``arz_*``); the relaxation's
     ``fsolve`` (arz.py:462-463) is replaced by the closed-form root of the same
     affine system (see oracle/np_oracle.py ``arz_step``).
 

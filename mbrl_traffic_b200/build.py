@@ -26,6 +26,11 @@ NVCC_FLAGS = [
 ]
 
 
+def extra_flags():
+    """MT_NVCC_FLAGS: extra compiler flags (experiment builds, e.g. -DMT_TRACE)."""
+    return os.environ.get("MT_NVCC_FLAGS", "").split()
+
+
 def needs_build():
     if not os.path.isfile(OUTPUT):
         return True
@@ -38,8 +43,11 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUTPUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", OUTPUT] + SOURCES
+    # compile next to the target and rename: a reader (or a snapshot of the
+    # tree) never sees a half-written library
+    tmp = OUTPUT + ".tmp.so"
+    cmd = [nvcc] + NVCC_FLAGS + extra_flags() + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", tmp] + SOURCES
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                           universal_newlines=True)
     if verbose or proc.returncode != 0:
@@ -47,6 +55,7 @@ def build(force=False, verbose=False):
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed (%d): %s" % (proc.returncode,
                                                      " ".join(cmd)))
+    os.replace(tmp, OUTPUT)
     return OUTPUT
 
 

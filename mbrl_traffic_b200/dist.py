@@ -55,6 +55,12 @@ class DomainDecomposedRoad(object):
         self.has_left = rank > 0
         self.has_right = rank < world - 1
         self.n_local = (self.hi - self.lo) + halo * (self.has_left + self.has_right)
+        physical = getattr(stepper, "physical", ())
+        if world > 1 and any(code == 0 for code in physical):   # MT_BC_LOOP
+            raise ValueError(
+                "the reference 'loop' rule copies cells of the road's far end "
+                "(lwr.py:237-244, arz.py:316-328), which a block of a decomposed "
+                "road does not hold: use extend / constant road ends")
         self.stepper = stepper
         self.exchange = exchange or self._torch_exchange
         self.peer = None               # a PeerHalo: exchange over peer memory instead
@@ -311,7 +317,7 @@ def engine_stepper(engine, physical_left, physical_right, left_val=(0.0, 0.0),
     road ends (``_lib.MT_BC_EXTEND`` / ``MT_BC_CONSTANT``)."""
     import torch
     from mbrl_traffic_b200 import _lib
-    state = {"bc": None, "buf": None}
+    state = {"bc": None, "bufs": None}
 
     def prepare(local_obs, bc_left, bc_right):
         cl = _lib.MT_BC_HALO if bc_left == "halo" else physical_left
@@ -322,21 +328,28 @@ def engine_stepper(engine, physical_left, physical_right, left_val=(0.0, 0.0),
                 **params)
             state["bc"] = (cl, cr)
         x = local_obs.reshape(1, -1)
-        if state["buf"] is None or state["buf"].data_ptr() == x.data_ptr():
-            state["buf"] = torch.empty_like(x)
-        return x, state["buf"]
+        # the stepper ping-pongs between two buffers of its own; a block handed
+        # in by the caller (the scattered initial state) is copied, never
+        # overwritten
+        if state["bufs"] is None:
+            state["bufs"] = [torch.empty_like(x), torch.empty_like(x)]
+        bufs = state["bufs"]
+        for i in (0, 1):
+            if bufs[i].data_ptr() == x.data_ptr():
+                return bufs[i], bufs[1 - i]
+        bufs[0].copy_(x)
+        return bufs[0], bufs[1]
 
     def step(local_obs, bc_left, bc_right):
         x, out = prepare(local_obs, bc_left, bc_right)
         engine.step(x, out)
-        state["buf"] = x          # ping-pong
         return out.reshape(local_obs.shape)
 
     def block(local_obs, k, bc_left, bc_right):
         x, other = prepare(local_obs, bc_left, bc_right)
         final = engine.rollout(x, other, k)
-        state["buf"] = other if final.data_ptr() == x.data_ptr() else x
         return final.reshape(local_obs.shape)
 
     step.block = block
+    step.physical = (physical_left, physical_right)
     return step

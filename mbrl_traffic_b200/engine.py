@@ -205,6 +205,14 @@ class Engine(object):
             self._h, _ptr(obs_pred), _ptr(obs_target), _ptr(out),
             _stream_ptr(stream)))
 
+    def overlap_stats(self, stream=None):
+        """``mt_overlap_stats`` of this engine's device and ``stream``:
+        ``(ctas_started, ctas_finished, ctas_run_without_waiting)``."""
+        out = (ctypes.c_uint64 * 3)()
+        _lib.check(self._lib.mt_overlap_stats(self.device, _stream_ptr(stream),
+                                              ctypes.byref(out)))
+        return int(out[0]), int(out[1]), int(out[2])
+
     @property
     def launch_count(self):
         out = ctypes.c_int64(0)

@@ -15,7 +15,8 @@ class LWRModel(FiniteVolumeModel):
     ``model.json`` schema are the reference's (lwr.py:56-138, 192-204,
     349-379).  The step itself -- Greenshields speed, demand/supply Godunov
     flux with the reference's per-cell ``q_max``, frozen cell 0 and the three
-    boundary modes (lwr.py:206-316) -- runs in ``lwr_step_vec_kernel``.
+    boundary modes (lwr.py:206-316) -- runs in ``mt::step_pipe_kernel<T, 0, ...>``
+    (csrc/mt_pipe.cuh; per-cell arithmetic in csrc/mt_cell.cuh ``lwr_*``).
 
     Extra keyword arguments (not in the reference): ``device``,
     ``action_is_speed_limit``, ``fast_math``.  ``rho_max``, ``v_max`` and

@@ -149,3 +149,121 @@ class GeneticAlgorithm(_PopulationOptimizer):
             if self.verbose >= 2 and it % 10 == 0:
                 print("GA it %d best %.6g" % (it, best_f))
         return best_x, best_f
+
+
+class NelderMead(_PopulationOptimizer):
+    """Nelder-Mead simplex search with the reference's constructor
+    (``optimizers/nelder_mead.py:22-79``: ``x0``, ``disp``,
+    ``initial_simplex``, ``xatol``, ``fatol``, ``adaptive``) and the moves and
+    bound handling of ``scipy.optimize.minimize(method="Nelder-Mead",
+    bounds=...)``, which the reference calls (``nelder_mead.py:81-95``).
+
+    Batched: the reflection, expansion and both contraction points of every
+    simplex are scored TOGETHER by one ``batch_fitness_fn`` call (one model
+    step over ``4 * n_starts`` candidate blocks) instead of up to two
+    sequential fitness calls; the accepted point is the one the sequential
+    rules pick, so a run with ``n_starts=1`` visits the same simplices as
+    SciPy.  ``n_starts > 1`` runs that many simplices side by side (the first
+    from ``x0``, the others from seeded random points of the box) and returns
+    the best vertex found -- the same kernel launch serves all of them.
+    """
+
+    def __init__(self, param_low, param_high, fitness_fn, verbose=2, x0=None,
+                 disp=True, initial_simplex=None, xatol=1e-8, fatol=1000,
+                 adaptive=False, n_starts=1, batch_fitness_fn=None, seed=None):
+        super(NelderMead, self).__init__(
+            param_low, param_high, fitness_fn, verbose, 4 * n_starts,
+            batch_fitness_fn, seed)
+        self.x0 = np.asarray(x0, dtype=np.float64) if x0 is not None \
+            else 0.5 * (self.low + self.high)
+        self.bnds = (param_low, param_high)
+        self.n_starts = int(n_starts)
+        self.options = {"disp": disp, "initial_simplex": initial_simplex,
+                        "xatol": xatol, "fatol": fatol, "adaptive": adaptive}
+
+    def _initial_simplices(self):
+        d = self.low.size
+        starts = [np.clip(self.x0, self.low, self.high)]
+        for _ in range(self.n_starts - 1):
+            starts.append(self.rng.uniform(self.low, self.high))
+        sims = np.empty((self.n_starts, d + 1, d))
+        for s, x0 in enumerate(starts):
+            if s == 0 and self.options["initial_simplex"] is not None:
+                sims[0] = np.asarray(self.options["initial_simplex"], dtype=np.float64)
+                continue
+            sims[s, 0] = x0                          # scipy: 5 % steps, 0.00025 from zero
+            for k in range(d):
+                y = x0.copy()
+                y[k] = 1.05 * y[k] if y[k] != 0 else 0.00025
+                sims[s, k + 1] = y
+        return np.clip(sims, self.low, self.high)
+
+    def solve(self, num_steps=1000, termination_fn=None):
+        d, s_n = self.low.size, self.n_starts
+        if self.options["adaptive"]:
+            rho, chi, psi, sigma = 1.0, 1 + 2.0 / d, 0.75 - 1.0 / (2 * d), 1 - 1.0 / d
+        else:
+            rho, chi, psi, sigma = 1.0, 2.0, 0.5, 0.5
+        xatol, fatol = self.options["xatol"], self.options["fatol"]
+        sim = self._initial_simplices()                         # (S, d+1, d)
+        fsim = self._score(sim.reshape(-1, d)).reshape(s_n, d + 1)
+        fsim = np.where(np.isfinite(fsim), fsim, np.inf)
+
+        def sort():
+            order = np.argsort(fsim, axis=1, kind="stable")
+            np.copyto(fsim, np.take_along_axis(fsim, order, axis=1))
+            np.copyto(sim, np.take_along_axis(sim, order[:, :, None], axis=1))
+
+        sort()
+        live = np.ones(s_n, dtype=bool)
+        # scipy counts the initial simplex as iteration 1 (``iterations = 1;
+        # while iterations < maxiter``): num_steps = maxiter, as the reference
+        # passes it (nelder_mead.py:84)
+        for it in range(max(int(num_steps) - 1, 0)):
+            conv = (np.abs(sim[:, 1:] - sim[:, :1]).max(axis=(1, 2)) <= xatol) & \
+                   (np.abs(fsim[:, :1] - fsim[:, 1:]).max(axis=1) <= fatol)
+            live &= ~conv
+            if not live.any():
+                break
+            xbar = sim[:, :-1].sum(axis=1) / d
+            worst = sim[:, -1]
+            clip = lambda x: np.clip(x, self.low, self.high)    # noqa: E731
+            xr = clip((1 + rho) * xbar - rho * worst)
+            xe = clip((1 + rho * chi) * xbar - rho * chi * worst)
+            xc = clip((1 + psi * rho) * xbar - psi * rho * worst)
+            xcc = clip((1 - psi) * xbar + psi * worst)
+            f = self._score(np.concatenate((xr, xe, xc, xcc)))  # one batched step
+            f = np.where(np.isfinite(f), f, np.inf).reshape(4, s_n)
+            fxr, fxe, fxc, fxcc = f
+            shrink = np.zeros(s_n, dtype=bool)
+            for s in np.nonzero(live)[0]:
+                if fxr[s] < fsim[s, 0]:
+                    if fxe[s] < fxr[s]:
+                        sim[s, -1], fsim[s, -1] = xe[s], fxe[s]
+                    else:
+                        sim[s, -1], fsim[s, -1] = xr[s], fxr[s]
+                elif fxr[s] < fsim[s, -2]:
+                    sim[s, -1], fsim[s, -1] = xr[s], fxr[s]
+                elif fxr[s] < fsim[s, -1]:
+                    if fxc[s] <= fxr[s]:
+                        sim[s, -1], fsim[s, -1] = xc[s], fxc[s]
+                    else:
+                        shrink[s] = True
+                else:
+                    if fxcc[s] < fsim[s, -1]:
+                        sim[s, -1], fsim[s, -1] = xcc[s], fxcc[s]
+                    else:
+                        shrink[s] = True
+            if shrink.any():
+                idx = np.nonzero(shrink)[0]
+                sim[idx, 1:] = clip(sim[idx, :1] + sigma * (sim[idx, 1:] - sim[idx, :1]))
+                fs = self._score(sim[idx, 1:].reshape(-1, d)).reshape(len(idx), d)
+                fsim[idx, 1:] = np.where(np.isfinite(fs), fs, np.inf)
+            sort()
+            best = float(fsim[:, 0].min())
+            if self.verbose >= 2 and it % 10 == 0:
+                print("NelderMead it %d best %.6g" % (it, best))
+            if termination_fn is not None and termination_fn(best):
+                break
+        s_best = int(np.argmin(fsim[:, 0]))
+        return sim[s_best, 0].copy(), float(fsim[s_best, 0])

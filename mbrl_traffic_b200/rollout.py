@@ -183,6 +183,10 @@ class KShootPolicy(object):
         all particles ``(B, num_particles)``."""
         if actions is None:
             actions = self.sample_actions()
+        # the model may have been refitted / reloaded since the last call
+        self.model._sync_params(
+            (self.n_envs * self.num_particles, self.n_cells, dtype_name(self.dtype),
+             self.model.device, False), self.engine)
         k = self.num_particles
         # every road's state to its k particles: one broadcasting copy
         self._a.view(self.n_envs, k, -1).copy_(obs[:, None, :].expand(-1, k, -1))
