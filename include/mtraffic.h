@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define MT_VERSION 110 /* 0.1.1 */
+#define MT_VERSION 100 /* 0.1.0 */
 
 typedef struct mt_engine mt_engine;
 
@@ -89,29 +89,19 @@ enum {
                              instead of the persistent TMA-pipelined one;
                              same results, for A/B measurements and tests  */
   MT_FLAG_INDEPENDENT_INPUT = 4
-                          /* accepted and ignored (version 1.0 needed it to
-                             overlap independent launches; the engine now
-                             finds out by itself: "Launch overlap" below)   */
+                          /* the caller guarantees that the INPUT batch of a
+                             step is not written by the work enqueued right
+                             before it on the stream (independent batches, a
+                             pool of buffers).  The step kernel then starts
+                             fetching its input while the previous launch
+                             still drains; its stores still wait for it.
+                             Same results.  Do NOT set it for chained steps
+                             (input = the previous step's output).  Used only
+                             when this launch and the engine's previous one
+                             on the stream both fill the GPU (anything older
+                             is then known to have finished), with scalar
+                             parameters and without speed limits / rewards. */
 };
-
-/* Launch overlap.  A step that fills the GPU (grid = every CTA slot) normally
- * starts only when the work enqueued before it on the stream has finished.
- * The library keeps, per device and stream, the byte ranges read and written
- * by the step it enqueued last; when the next step neither reads nor writes a
- * byte that one writes, and writes no byte it reads (independent batches: a
- * pool of buffers, compute_loss rows, K-shoot particles), its CTAs take over
- * SM slots as the earlier step's CTAs retire instead of waiting for the whole
- * grid.  The decision is re-checked on the device: a CTA skips the wait only
- * if it SEES that earlier step still running (its completion counter has not
- * reached the grid size), which proves that nothing else was enqueued between
- * the two on the stream -- a memcpy, a memset or a kernel of another library
- * would have waited for the earlier step to finish -- and that everything
- * older has finished.  Results are identical either way.
- * The one thing the check cannot see is foreign work that was itself launched
- * with cudaLaunchAttributeProgrammaticStreamSerialization: do not enqueue
- * such launches between two mt_step calls on buffers the steps use.  Captured
- * graphs must be replayed on one stream at a time.  MT_OVERLAP=0 in the
- * environment turns the mechanism off. */
 
 /* Fixed for the life of an engine. */
 typedef struct mt_config {
@@ -233,12 +223,6 @@ int mt_halo_push(mt_halo *h, void *local, int64_t n_local, void *stream);
 int mt_halo_pull(mt_halo *h, void *local, int64_t n_local, void *stream);
 /* Synchronises the device; *timed_out = 1 if a pull gave up waiting. */
 int mt_halo_status(mt_halo *h, int32_t *timed_out);
-
-/* Launch-overlap statistics of one stream of a device (synchronous copy):
- * out[0] = CTAs of participating launches started, out[1] = finished,
- * out[2] = CTAs that ran without waiting for the previous launch.  All zero
- * before the first participating launch.  See "Launch overlap" above. */
-int mt_overlap_stats(int32_t device, void *stream, uint64_t out[3]);
 
 /* Number of kernels this engine has launched so far. */
 int mt_launch_count(const mt_engine *e, int64_t *out);

@@ -11,7 +11,7 @@ the tests at tests/fast_tests/test_models.py:100-162 assign them directly).
 import numpy as np
 
 from mbrl_traffic_b200.base import Model
-from mbrl_traffic_b200.engine import Engine, dtype_name
+from mbrl_traffic_b200.engine import Engine, PinnedPool, dtype_name
 
 
 def _is_torch(x):
@@ -42,6 +42,7 @@ class FiniteVolumeModel(Model):
         self._engines = {}
         self._param_keys = {}
         self._pop_cache = {}
+        self._pinned = None
 
     # ------------------------------------------------------------------ #
     # reference-compatible no-ops                                        #
@@ -145,7 +146,11 @@ class FiniteVolumeModel(Model):
             raise ValueError("obs must be (2N,) or (batch, 2N)")
         n_envs, n_cells = batch.shape[0], batch.shape[1] // 2
         eng = self._get_engine(n_envs, n_cells, batch.dtype.name, host=True)
-        out = np.empty_like(batch)
+        # a NEW array per call, as in the reference -- on a recycled page-locked
+        # block, so that the download runs at the PCIe rate (engine.PinnedPool)
+        if self._pinned is None:
+            self._pinned = PinnedPool()
+        out = self._pinned.take(batch.shape, batch.dtype)
         act = None
         if action is not None:
             act = np.ascontiguousarray(
@@ -299,6 +304,8 @@ class FiniteVolumeModel(Model):
             eng.close()
         for ws in self._pop_cache.values():
             ws["eng"].close()
+        if self._pinned is not None:
+            self._pinned.drain()
         self._engines = {}
         self._param_keys = {}
         self._pop_cache = {}

@@ -26,7 +26,6 @@ EXPORTS = (
     "mt_launch_count", "mt_alloc_pinned", "mt_free_pinned", "mt_aggregate",
     "mt_nonfinite", "mt_halo_create", "mt_halo_destroy", "mt_halo_handle", "mt_halo_connect",
     "mt_halo_connect_local", "mt_halo_push", "mt_halo_pull", "mt_halo_status",
-    "mt_overlap_stats",
 )
 
 
@@ -101,8 +100,6 @@ def load():
     lib.mt_aggregate.restype = ctypes.c_int
     lib.mt_aggregate.argtypes = [vp, vp, vp, i64, ctypes.c_double, ctypes.c_double,
                                  i32, i32, ctypes.c_double, vp, vp, vp, i32, vp]
-    lib.mt_overlap_stats.restype = ctypes.c_int
-    lib.mt_overlap_stats.argtypes = [i32, vp, ctypes.POINTER(ctypes.c_uint64 * 3)]
     lib.mt_launch_count.restype = ctypes.c_int
     lib.mt_launch_count.argtypes = [vp, ctypes.POINTER(i64)]
     lib.mt_alloc_pinned.restype = ctypes.c_int

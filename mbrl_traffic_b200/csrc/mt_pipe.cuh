@@ -27,11 +27,8 @@
 // Tile schedule: static round-robin, or (HBM-bound instantiations, large
 // batches) tiles drawn from a per-engine counter -- see PipeDynamic.
 // Launch boundary: programmatic dependent launch; before waiting for the
-// previous launch the producer prefetches its first tiles towards L2.  Launches
-// that fill every CTA slot of the GPU take part in the launch-overlap protocol
-// (PipeArgs::ovl): a launch the host has shown to be independent of the one
-// before it does not wait for it at all -- its CTAs take over SM slots as that
-// launch's CTAs retire and the GPU never drains between steps.
+// previous launch the producer prefetches its first tiles towards L2, and with
+// MT_FLAG_INDEPENDENT_INPUT it issues the first ring-full of loads outright.
 #pragma once
 #include <stdint.h>
 #include "mtraffic.h"
@@ -143,6 +140,20 @@ __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src_gme
       "l"(src_gmem), "r"(bytes), "r"(bar)
       : "memory");
 }
+// the same load with an L2 eviction-priority hint (createpolicy operand)
+__device__ __forceinline__ void bulk_load_hint(uint32_t dst_smem, const void* src_gmem,
+                                               uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+      "l"(src_gmem), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 // shared -> global, tracked by the per-thread bulk async-group
 __device__ __forceinline__ void bulk_store(void* dst_gmem, uint32_t src_smem, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
@@ -168,27 +179,6 @@ __device__ __forceinline__ void pdl_launch_dependents() {
 }
 __device__ __forceinline__ void pdl_wait_prior_grid() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
-}
-// completion (not just the shared-memory read) of all but the newest N bulk stores
-template <int N> __device__ __forceinline__ void bulk_wait_all() {
-  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
-}
-// orders generic-proxy accesses to global memory with the bulk engine's
-__device__ __forceinline__ void fence_proxy_async_global() {
-  asm volatile("fence.proxy.async.global;" ::: "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed_gpu(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 // barrier among the consumer threads only (id 1; id 0 is __syncthreads)
 __device__ __forceinline__ void consumer_sync(int nc) {
@@ -280,33 +270,14 @@ template <typename T> struct PipeArgs {
   // each CTA's first ring-full, sched[1] counts finished CTAs (the last one
   // re-arms both).  nullptr: static round-robin schedule.
   unsigned int* sched = nullptr;
+  // The input batch was not written by the launch this one programmatically
+  // depends on: the first ring-full of loads is issued BEFORE waiting for that
+  // launch to finish (only the stores wait), so this launch's pipeline fills
+  // while the previous one drains.  See MT_FLAG_INDEPENDENT_INPUT.
+  int early_loads = 0;
   int early_l2 = 2;  // tiles per CTA pulled towards L2 before the grid-dependency wait
-  // ---- launch-overlap protocol (host side: OverlapSlot in mtraffic.cu) -------
-  // ovl != nullptr: this launch fills every CTA slot of the GPU (grid == slots)
-  // and takes part.  ovl points at the stream's counter block in device memory:
-  //   ovl[OVL_ARRIVED]  CTAs of participating launches that have started
-  //   ovl[OVL_DONE]     CTAs whose stores have completed
-  //   ovl[OVL_SIG + (seq & 3)]  signature of launch number seq
-  //   ovl[OVL_FREE_RUNS]  CTAs that ran without waiting (statistics)
-  // A CTA's ticket from ovl[OVL_ARRIVED] gives its launch number seq = ticket /
-  // grid (the next launch's CTAs only start once every CTA of this one has
-  // taken its ticket: the trigger follows the ticket).  ovl_mode says what the
-  // HOST knows about the launch enqueued right before this one on the stream:
-  //   OVL_WAIT  nothing: wait for it (griddepcontrol.wait)
-  //   OVL_FREE  it was the participating launch with signature ovl_pred_sig,
-  //             and neither launch touches a byte the other one writes
-  // The kernel acts on OVL_FREE only when it SEES that launch still running
-  // (ovl[OVL_DONE] < seq * grid) with the expected signature and everything
-  // older finished (ovl[OVL_DONE] >= (seq - 1) * grid).  A predecessor that is
-  // still running proves that no other work sits between the two launches on
-  // the stream: any such work would have waited for its completion (see
-  // mtraffic.h, "Launch overlap").  In every other case the CTA waits.
-  unsigned long long* ovl = nullptr;
-  unsigned long long ovl_sig = 0, ovl_pred_sig = 0;
-  int ovl_mode = 0;
+  int l2_hint = 0;   // != 0: tile loads carry L2::evict_first (a tile is read once per step)
 };
-enum { OVL_ARRIVED = 0, OVL_DONE = 16, OVL_SIG = 32, OVL_FREE_RUNS = 48, OVL_WORDS = 64 };  // u64 words; 128-byte lines
-enum { OVL_WAIT = 0, OVL_FREE = 1 };
 
 // Which instantiations of step_pipe_kernel draw their tiles from a counter.
 // Measured on B200: the HBM-bound ones gain (LWR f64 83% ->
@@ -357,19 +328,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
     a.trace[(size_t)blockIdx.x * 8 + 7] = smid;
   }
 #endif
-  // Launch-overlap protocol: the producer thread draws this CTA's ticket first
-  // thing (the round trip overlaps the set-up below) and triggers the dependent
-  // launch only once it holds the ticket; every other launch triggers at once.
-  const bool ovl = a.ovl != nullptr;
-  unsigned long long ticket = 0, done0 = 0;
-  if (ovl) {
-    if (t == NC) {
-      ticket = atomicAdd(a.ovl + OVL_ARRIVED, 1ULL);
-      done0 = ld_acquire_gpu(a.ovl + OVL_DONE);
-    }
-  } else {
-    pdl_launch_dependents();
-  }
+  pdl_launch_dependents();
   // pad slots of the exchange arrays stay zero for the kernel's life: they
   // feed the (discarded) left-face flux of each road's first cell
   for (int i = t; i < 2 * PIPE_XCH; i += blockDim.x) { (&sm.xD[0][0])[i] = T(0); (&sm.xR[0][0])[i] = T(0); }
@@ -386,8 +345,9 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
   }
   __syncthreads();
   // everything above overlapped the previous kernel's tail
+  const bool early = a.early_loads != 0;
 #ifndef MT_NO_EARLY_L2
-  if (t == NC) {
+  if (!early && t == NC) {
     // The loads themselves must wait for the previous launch (its output may be
     // this launch's input), but an L2 prefetch is not a read: it returns no
     // data, and L2 is the point of coherence, so lines the previous launch
@@ -408,39 +368,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
     }
   }
 #endif
-  if (!ovl) {
-    pdl_wait_prior_grid();
-  } else if (t == NC) {
-    const unsigned long long G = gridDim.x;
-    const unsigned long long seq = ticket / G;   // this launch's number on the stream
-    st_relaxed_gpu(a.ovl + OVL_SIG + (seq & 3), a.ovl_sig);
-    __threadfence();            // ticket and signature are performed before the trigger
-    pdl_launch_dependents();
-    bool free_run = false;
-    if (a.ovl_mode == OVL_FREE && seq > 0) {
-      const unsigned long long pred = ld_relaxed_gpu(a.ovl + OVL_SIG + ((seq - 1) & 3));
-      free_run = pred == a.ovl_pred_sig && done0 < seq * G && done0 >= (seq - 1) * G;
-    }
-    if (free_run) atomicAdd(a.ovl + OVL_FREE_RUNS, 1ULL);   // (statistics: mt_overlap_stats)
-    if (!free_run) {
-      pdl_wait_prior_grid();
-      // The wait covers the launch right before this one only, and that launch
-      // may itself have run ahead of ITS predecessor: make sure every earlier
-      // participating launch has finished as well (it has, but for a straggling
-      // CTA; bounded so that a misused engine cannot hang the GPU).
-      if (ld_acquire_gpu(a.ovl + OVL_DONE) < seq * G) {
-        unsigned long long t0, t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        do {
-          __nanosleep(200);
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        } while (ld_acquire_gpu(a.ovl + OVL_DONE) < seq * G && t1 - t0 < 5000000ULL);
-      }
-    }
-    fence_proxy_async_global();  // acquired completions -> the bulk engine's reads
-  } else if (a.ovl_mode == OVL_WAIT) {
-    pdl_wait_prior_grid();      // consumers read per-road constants / speed limits themselves
-  }
+  if (!early) pdl_wait_prior_grid();
 
   // ======================= producer warp ===================================
   if (t >= NC) {
@@ -450,6 +378,12 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
       auto bytes_of = [&](int tile) -> uint32_t {
         return tile == last_tile ? (uint32_t)last_envs * row_bytes : tile_bytes;
       };
+      const bool hint_ld = a.l2_hint != 0;
+      const uint64_t pol_ld = hint_ld ? l2_policy_evict_first() : 0;
+      auto tile_load = [&](uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+        if (hint_ld) bulk_load_hint(dst, src, bytes, bar, pol_ld);
+        else bulk_load(dst, src, bytes, bar);
+      };
       if constexpr (!DYN) {
         auto issue_load = [&](int i) {
           const int tile = (int)blockIdx.x + i * (int)gridDim.x;
@@ -457,7 +391,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
           if (ARZ) {
             const uint32_t bytes = bytes_of(tile);
             mbar_expect_tx(full0 + 8 * s, bytes);
-            bulk_load(in0 + (uint32_t)s * PIPE_TILE_BYTES, gin + (size_t)tile * tile_bytes, bytes,
+            tile_load(in0 + (uint32_t)s * PIPE_TILE_BYTES, gin + (size_t)tile * tile_bytes, bytes,
                       full0 + 8 * s);
           } else {
             // LWR ignores the input velocity (lwr.py:197): fetch the density half
@@ -466,7 +400,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
             const uint32_t half = row_bytes >> 1;
             mbar_expect_tx(full0 + 8 * s, (uint32_t)envs * half);
             for (int r = 0; r < envs; ++r)
-              bulk_load(in0 + (uint32_t)s * PIPE_TILE_BYTES + (uint32_t)r * row_bytes,
+              tile_load(in0 + (uint32_t)s * PIPE_TILE_BYTES + (uint32_t)r * row_bytes,
                         gin + (size_t)tile * tile_bytes + (size_t)r * row_bytes, half,
                         full0 + 8 * s);
           }
@@ -486,6 +420,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
         for (int i = 0; i < pre; ++i) issue_load(i);
         const int ahead = a.l2_ahead;
         for (int i = PIPE_STAGES; i < PIPE_STAGES + ahead && i < n_my; ++i) prefetch(i);
+        if (early) pdl_wait_prior_grid();   // before the first store
         for (int i = 0; i < n_my; ++i) {
           const int tile = (int)blockIdx.x + i * (int)gridDim.x;
           const int s = i % PIPE_STAGES, o = i % PIPE_OUT;
@@ -528,7 +463,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
           if (ARZ) {
             const uint32_t bytes = bytes_of(tile);
             mbar_expect_tx(full0 + 8 * s, bytes);
-            bulk_load(in0 + (uint32_t)s * PIPE_TILE_BYTES, gin + (size_t)tile * tile_bytes, bytes,
+            tile_load(in0 + (uint32_t)s * PIPE_TILE_BYTES, gin + (size_t)tile * tile_bytes, bytes,
                       full0 + 8 * s);
           } else {
             // LWR ignores the input velocity (lwr.py:197): fetch the density half
@@ -537,7 +472,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
             const uint32_t half = row_bytes >> 1;
             mbar_expect_tx(full0 + 8 * s, (uint32_t)envs * half);
             for (int r = 0; r < envs; ++r)
-              bulk_load(in0 + (uint32_t)s * PIPE_TILE_BYTES + (uint32_t)r * row_bytes,
+              tile_load(in0 + (uint32_t)s * PIPE_TILE_BYTES + (uint32_t)r * row_bytes,
                         gin + (size_t)tile * tile_bytes + (size_t)r * row_bytes, half,
                         full0 + 8 * s);
           }
@@ -555,6 +490,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
         };
         MT_STAMP(1);
         for (int s = 0; s < PIPE_STAGES; ++s) issue_load(s, grab());
+        if (early) pdl_wait_prior_grid();   // before the first store and the first counter draw
         // tiles drawn and prefetched into L2 but not yet loaded: a ring in
         // shared memory (this thread only), oldest at index i % PIPE_QMAX
         const int ahead = a.l2_ahead < PIPE_QMAX ? a.l2_ahead : PIPE_QMAX;
@@ -598,13 +534,6 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
         }
       }
       bulk_wait_read<0>();  // shared memory must outlive the last bulk store
-      if (ovl) {
-        // this CTA's results are in global memory: count it as finished
-        bulk_wait_all<0>();
-        fence_proxy_async_global();
-        __threadfence();
-        atomicAdd(a.ovl + OVL_DONE, 1ULL);
-      }
       MT_STAMP(6);
     }
     return;

@@ -205,14 +205,6 @@ class Engine(object):
             self._h, _ptr(obs_pred), _ptr(obs_target), _ptr(out),
             _stream_ptr(stream)))
 
-    def overlap_stats(self, stream=None):
-        """``mt_overlap_stats`` of this engine's device and ``stream``:
-        ``(ctas_started, ctas_finished, ctas_run_without_waiting)``."""
-        out = (ctypes.c_uint64 * 3)()
-        _lib.check(self._lib.mt_overlap_stats(self.device, _stream_ptr(stream),
-                                              ctypes.byref(out)))
-        return int(out[0]), int(out[1]), int(out[2])
-
     @property
     def launch_count(self):
         out = ctypes.c_int64(0)
@@ -239,3 +231,68 @@ class PinnedArray(object):
             self.array = None
             self._lib.mt_free_pinned(self._p)
             self._p = None
+
+
+class _PinnedBlock(object):
+    """Owner object of one page-locked block handed out by ``PinnedPool``; the
+    NumPy array built on it (and every view of that array) keeps it alive
+    through ``ndarray.base``.  When the last of them is gone the block goes
+    back to the pool."""
+
+    def __init__(self, pool, ptr, nbytes, shape, dtype):
+        self._pool, self._ptr, self._nbytes = pool, ptr, nbytes
+        self.__array_interface__ = {
+            "shape": tuple(shape), "typestr": np.dtype(dtype).str,
+            "data": (ptr, False), "version": 3}
+
+    def __del__(self):
+        pool = self._pool
+        if pool is not None:
+            pool._give_back(self._ptr, self._nbytes)
+
+
+class PinnedPool(object):
+    """Page-locked result buffers for the host path of ``get_next_obs``.
+
+    ``cudaMallocHost`` costs milliseconds, a device-to-host copy into pageable
+    memory runs at a fraction of the PCIe rate; the reference contract wants a
+    NEW array from every call (base.py:58-74).  ``take`` returns a fresh NumPy
+    array on a page-locked block; the block is recycled once the caller has
+    dropped the array and all of its views, so a loop that keeps only the
+    latest observation allocates twice and then never again, and an array the
+    caller still holds is never overwritten.  At most ``keep`` idle blocks per
+    size are kept; the rest are freed.
+    """
+
+    def __init__(self, keep=3):
+        self._lib = _lib.load()
+        self._free = {}
+        self._keep = keep
+
+    def take(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        nbytes = max(int(np.prod(shape)) * dtype.itemsize, 1)
+        idle = self._free.get(nbytes)
+        if idle:
+            ptr = idle.pop()
+        else:
+            p = ctypes.c_void_p()
+            _lib.check(self._lib.mt_alloc_pinned(nbytes, ctypes.byref(p)))
+            ptr = p.value
+        return np.asarray(_PinnedBlock(self, ptr, nbytes, shape, dtype))
+
+    def _give_back(self, ptr, nbytes):
+        idle = self._free.setdefault(nbytes, [])
+        if len(idle) < self._keep:
+            idle.append(ptr)
+        else:
+            try:
+                self._lib.mt_free_pinned(ctypes.c_void_p(ptr))
+            except Exception:
+                pass
+
+    def drain(self):
+        """Free every idle block."""
+        for idle in self._free.values():
+            while idle:
+                self._lib.mt_free_pinned(ctypes.c_void_p(idle.pop()))
