@@ -101,43 +101,77 @@ class FeedForwardActor(nn.Module):
         return (0.5 * self.v_max_max) * (torch.tanh(x.squeeze(-1)) + 1.0)
 
 
+class PolicyRollout(object):
+    """``actor`` rolled through ``env``, captured ONCE as a CUDA graph of two
+    consecutive (policy, step, reward) iterations -- one per ping-pong
+    direction of the environment's state buffers -- and replayed for every
+    rollout after that: the loop has no per-step launch cost and no capture
+    cost after the first call (the caller of evaluate_model.py:388-403 rolls
+    the same policy out again and again)."""
+
+    def __init__(self, env, actor):
+        self.env, self.actor = env, actor
+        self.total = torch.zeros(env.n_envs, dtype=env.dtype, device=env.device)
+        self.stream = torch.cuda.Stream(device=env.device)
+        self.graph = None
+
+    def _one(self):
+        env = self.env
+        with torch.no_grad():
+            act = self.actor(env.obs).to(env.dtype).contiguous()
+        _, r, _, _ = env.step(act)
+        self.total.add_(r)
+
+    def _capture(self):
+        env = self.env
+        with torch.cuda.stream(self.stream):
+            self._one()
+            self._one()                         # warm-up both directions
+            torch.cuda.synchronize(env.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=self.stream):
+                self._one()
+                self._one()
+
+    def run(self, obs0, horizon=None):
+        """Sum of rewards per road over ``horizon`` steps from ``obs0``
+        (device tensor, overwritten by the next call)."""
+        env = self.env
+        horizon = env.horizon if horizon is None else horizon
+        if self.graph is None:
+            self.stream.wait_stream(torch.cuda.current_stream(env.device))
+            with torch.cuda.stream(self.stream):
+                env.reset(obs0)
+            self._capture()
+        self.stream.wait_stream(torch.cuda.current_stream(env.device))
+        with torch.cuda.stream(self.stream):
+            env.reset(obs0)
+            self.total.zero_()
+            done = 0
+            while done + 2 <= horizon:
+                self.graph.replay()
+                done += 2
+            for _ in range(horizon - done):
+                self._one()
+        torch.cuda.current_stream(env.device).wait_stream(self.stream)
+        return self.total
+
+
 def policy_rollout(env, actor, obs0, horizon=None, use_graph=True):
     """Roll ``actor`` through ``env`` for ``horizon`` steps; returns the sum
-    of rewards per road (device tensor).  With ``use_graph`` two consecutive
-    (policy, step) iterations -- one per ping-pong direction -- are captured
-    in a CUDA graph and replayed, so the loop has no per-step launch cost."""
+    of rewards per road (device tensor).  With ``use_graph`` the loop runs as
+    replays of a two-step CUDA graph (``PolicyRollout``; keep that object to
+    amortise the capture over many rollouts)."""
     horizon = env.horizon if horizon is None else horizon
+    if use_graph and horizon >= 4:
+        return PolicyRollout(env, actor).run(obs0, horizon)
     env.reset(obs0)
     total = torch.zeros(env.n_envs, dtype=env.dtype, device=env.device)
-
-    def one():
+    for _ in range(horizon):
         with torch.no_grad():
             act = actor(env.obs).to(env.dtype).contiguous()
         _, r, _, _ = env.step(act)
         total.add_(r)
-
-    if not use_graph or horizon < 4:
-        for _ in range(horizon):
-            one()
-        return total
-
-    stream = torch.cuda.Stream(device=env.device)
-    stream.wait_stream(torch.cuda.current_stream(env.device))
-    with torch.cuda.stream(stream):
-        one()
-        one()                                   # warm-up both directions
-        torch.cuda.synchronize(env.device)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=stream):
-            one()
-            one()
-        done = 2
-        while done + 2 <= horizon:
-            graph.replay()
-            done += 2
-        for _ in range(horizon - done):
-            one()
-    torch.cuda.current_stream(env.device).wait_stream(stream)
     return total
 
 
