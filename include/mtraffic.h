@@ -160,7 +160,9 @@ int mt_step(mt_engine *e, const void *obs_in, const void *action,
  * DEVICE [n_steps, B] or NULL.  *result_in_b is set to 1 when the final state
  * is in obs_b, else 0; the other batch is scratch.  Batches whose roads fit
  * one tile run as ONE launch (state in registers between steps, one HBM read
- * and write per road); results are bit-identical to n_steps mt_step calls. */
+ * and write per road); longer roads (without rewards, without the LOOP rule)
+ * advance as overlapping windows, 16 steps per launch; results are
+ * bit-identical to n_steps mt_step calls. */
 int mt_rollout(mt_engine *e, void *obs_a, void *obs_b, const void *actions,
                void *rewards, int32_t n_steps, void *stream,
                int32_t *result_in_b);
@@ -221,6 +223,21 @@ int mt_halo_connect(mt_halo *h, const unsigned char *left_handle,
 int mt_halo_connect_local(mt_halo *h, mt_halo *left, mt_halo *right);
 int mt_halo_push(mt_halo *h, void *local, int64_t n_local, void *stream);
 int mt_halo_pull(mt_halo *h, void *local, int64_t n_local, void *stream);
+/* n_steps steps of a rank's block with the ghost-cell exchange folded into the
+ * step launches: every `halo` steps are ONE launch that fetches the ghost
+ * cells from this rank's mailbox (after waiting for the neighbours' flags,
+ * unless ghosts_fresh says the block's ghost cells are current, as right after
+ * a scatter or an explicit exchange), advances overlapping windows of the block
+ * on chip, and stores the block's first / last `halo` own cells straight into
+ * the neighbours' mailboxes with the epoch flag.  Equivalent to n_steps
+ * mt_step calls with mt_halo_push / mt_halo_pull every `halo` steps; on return
+ * the ghost cells are stale and one push is pending (the next call pulls it).
+ * The engine holds one road block (n_envs == 1, MT_BC_HALO on every edge that
+ * has a neighbour) too long for the one-tile kernels; halo * sizeof(dtype)
+ * must be a multiple of 16.  Every rank issues the same sequence of calls. */
+int mt_halo_advance(mt_engine *e, mt_halo *h, void *obs_a, void *obs_b,
+                    int32_t n_steps, int32_t ghosts_fresh, void *stream,
+                    int32_t *result_in_b);
 /* Synchronises the device; *timed_out = 1 if a pull gave up waiting. */
 int mt_halo_status(mt_halo *h, int32_t *timed_out);
 

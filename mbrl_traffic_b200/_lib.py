@@ -26,6 +26,7 @@ EXPORTS = (
     "mt_launch_count", "mt_alloc_pinned", "mt_free_pinned", "mt_aggregate",
     "mt_nonfinite", "mt_halo_create", "mt_halo_destroy", "mt_halo_handle", "mt_halo_connect",
     "mt_halo_connect_local", "mt_halo_push", "mt_halo_pull", "mt_halo_status",
+    "mt_halo_advance",
 )
 
 
@@ -122,6 +123,8 @@ def load():
     lib.mt_halo_push.argtypes = [vp, vp, i64, vp]
     lib.mt_halo_pull.restype = ctypes.c_int
     lib.mt_halo_pull.argtypes = [vp, vp, i64, vp]
+    lib.mt_halo_advance.restype = ctypes.c_int
+    lib.mt_halo_advance.argtypes = [vp, vp, vp, vp, i32, i32, vp, ctypes.POINTER(i32)]
     lib.mt_halo_status.restype = ctypes.c_int
     lib.mt_halo_status.argtypes = [vp, ctypes.POINTER(i32)]
     _lib = lib

@@ -171,6 +171,10 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t 
 template <int N> __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
+// completion (not just the shared-memory read) of all but the newest N bulk stores
+template <int N> __device__ __forceinline__ void bulk_wait_all() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
 // Programmatic dependent launch: let the next kernel in the stream start its
 // prologue while this one drains, and block until the previous kernel's
 // writes are visible.  Both are no-ops for an ordinary launch.

@@ -16,10 +16,11 @@
 #include "mt_ring.cuh"
 #include "mt_fused.cuh"
 #include "mt_seg.cuh"
+#include "mt_halo.cuh"
+#include "mt_segfused.cuh"
 #include "mt_direct.cuh"
 #include "mt_nonlocal.cuh"
 #include "mt_aggregate.cuh"
-#include "mt_halo.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -539,6 +540,143 @@ int launch_seg_fast(const SegArgs<T>& sa, int grid, bool fast, bool uniform, int
   return launch_seg_spec<T, MODEL, false, U>(sa, grid, uniform, lamk, s);
 }
 
+// ---- long roads, several steps per launch (mt_segfused.cuh) -----------------
+template <typename T, int MODEL, bool FAST, int LAMK, bool UNIFORM, int U>
+int launch_segfused(const SegFusedArgs<T>& sa, int grid, cudaStream_t stream) {
+  static bool configured_dev[MAX_DEVICES] = {};
+  bool* cfg_flag = configured_flag(configured_dev);
+  bool unused_flag = false;
+  bool& configured = cfg_flag ? *cfg_flag : unused_flag;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(step_segfused_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(PipeSmem<T, U>)));
+    configured = true;
+  }
+  return launch_pdl(step_segfused_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>, sa, grid, sa.nc + 32,
+                    sizeof(PipeSmem<T, U>), stream);
+}
+
+template <typename T, int MODEL, bool FAST, int U>
+int launch_segfused_spec(const SegFusedArgs<T>& sa, int grid, bool uniform, int lamk,
+                         cudaStream_t s) {
+  if (uniform && lamk == LAM_ONE && sa.u.rho_max == T(1))
+    return launch_segfused<T, MODEL, FAST, LAM_ONE_RM1, true, U>(sa, grid, s);
+  return launch_segfused<T, MODEL, FAST, LAM_RUNTIME, false, U>(sa, grid, s);
+}
+
+template <typename T, int MODEL, int U>
+int launch_segfused_fast(const SegFusedArgs<T>& sa, int grid, bool fast, bool uniform, int lamk,
+                         cudaStream_t s) {
+  if constexpr (FastAllowed<T>::value) {
+    if (fast) return launch_segfused_spec<T, MODEL, true, U>(sa, grid, uniform, lamk, s);
+  }
+  return launch_segfused_spec<T, MODEL, false, U>(sa, grid, uniform, lamk, s);
+}
+
+// Largest number of steps one launch of the window kernel may fuse: the
+// overlap 2 * roundup4(k) must leave at least half of a window.
+constexpr int SEGFUSED_MAX_STEPS = 128;
+
+// Window geometry of the several-steps-per-launch kernel for this engine, or
+// false when it does not apply (short roads take step_fused_kernel, the LOOP
+// rule needs the road's far end, the non-local model has its own kernel).
+template <typename T>
+bool segfused_geometry(const mt_engine* e, const void* obs_in, const void* obs_out, int& U,
+                       int& nc, int& window) {
+  constexpr int V = Vec<T>::N;
+  const mt_params& p = e->params;
+  const int N = (int)e->cfg.n_cells;
+  if (e->cfg.model == MT_MODEL_NONLOCAL || (p.flags & MT_FLAG_NO_PIPELINE)) return false;
+  if (p.bc_left == MT_BC_LOOP || p.bc_right == MT_BC_LOOP) return false;
+  const bool aligned = (((uintptr_t)obs_in | (uintptr_t)obs_out) & 15u) == 0;
+  const Geometry g = plan(e->cfg.n_envs, N, V, aligned);
+  if (!g.vector_ok || g.tiles <= 1) return false;
+  if (N % 4 != 0) return false;                 // window starts must stay 16-byte aligned
+  U = pipe_vectors_per_thread();
+  if (U == 0) U = (sizeof(T) == 8) ? 2 : 1;
+  nc = PIPE_BLOCK / U;
+  window = nc * U * V;
+  if (N <= window) return false;
+  const char* off = getenv("MT_NO_FUSE");
+  return !(off && off[0] == '1');
+}
+
+// n_inner steps of the whole batch in one launch of the window kernel.
+template <typename T>
+int segfused_typed(mt_engine* e, const void* obs_in_, const void* action_, long long action_stride,
+                   void* obs_out_, int n_inner, const SegHalo* hx, cudaStream_t stream) {
+  int U = 0, nc = 0, window = 0;
+  if (!segfused_geometry<T>(e, obs_in_, obs_out_, U, nc, window))
+    return fail(MT_EINVAL, "the several-steps-per-launch kernel does not apply to this engine");
+  if (n_inner < 1 || n_inner > SEGFUSED_MAX_STEPS)
+    return fail(MT_EINVAL, "steps per launch must be in [1, %d]", SEGFUSED_MAX_STEPS);
+  const mt_params& p = e->params;
+  const int N = (int)e->cfg.n_cells;
+  const long long B = e->cfg.n_envs;
+  SegFusedArgs<T> sa;
+  sa.in = (const T*)obs_in_; sa.out = (T*)obs_out_;
+  sa.table = (const T*)e->table; sa.flags = e->flags;
+  sa.action = (const T*)action_; sa.action_stride = action_stride;
+  sa.B = (int)B; sa.N = N; sa.nc = nc; sa.n_inner = n_inner;
+  sa.hh = (n_inner + 3) & ~3;
+  sa.tiles_per_row = segfused_tiles_per_row(N, window, sa.hh);
+  const long long n_tiles = B * (long long)sa.tiles_per_row;
+  if (n_tiles > 0x7fffffffLL) return fail(MT_EINVAL, "batch too large for one launch");
+  sa.n_tiles = (int)n_tiles;
+  sa.bc.bc_l = p.bc_left; sa.bc.bc_r = p.bc_right;
+  sa.bc.bl0 = (T)p.bc_left_val[0]; sa.bc.bl1 = (T)p.bc_left_val[1];
+  sa.bc.br0 = (T)p.bc_right_val[0]; sa.bc.br1 = (T)p.bc_right_val[1];
+  sa.step = (T)(p.dt / p.dx);
+  sa.u = uniform_of<T>(e);
+  if (hx) {
+    sa.halo = *hx;
+    const int h = hx->halo;
+    if (h * (int)sizeof(T) % 16 != 0 || 2 * h + sa.hh > window || n_inner > h)
+      return fail(MT_EINVAL, "halo %d does not fit the window kernel (steps %d, window %d)", h,
+                  n_inner, window);
+  }
+  const bool fast = FastAllowed<T>::value && (p.flags & MT_FLAG_FAST_MATH) != 0;
+  const long long slots = (long long)PIPE_CTAS * e->sm_count;
+  const int grid = (int)(n_tiles < slots ? n_tiles : slots);
+  int rc;
+  if (e->cfg.model == MT_MODEL_ARZ)
+    rc = U == 2 ? launch_segfused_fast<T, 1, 2>(sa, grid, fast, e->uniform, e->lamk, stream)
+                : launch_segfused_fast<T, 1, 1>(sa, grid, fast, e->uniform, e->lamk, stream);
+  else
+    rc = U == 2 ? launch_segfused_fast<T, 0, 2>(sa, grid, fast, e->uniform, e->lamk, stream)
+                : launch_segfused_fast<T, 0, 1>(sa, grid, fast, e->uniform, e->lamk, stream);
+  if (rc != MT_OK) return rc;
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return MT_OK;
+}
+
+int segfused_any(mt_engine* e, const void* obs_in, const void* action, long long action_stride,
+                 void* obs_out, int n_inner, const SegHalo* hx, cudaStream_t stream) {
+  if (e->cfg.dtype == MT_F64)
+    return segfused_typed<double>(e, obs_in, action, action_stride, obs_out, n_inner, hx, stream);
+  return segfused_typed<float>(e, obs_in, action, action_stride, obs_out, n_inner, hx, stream);
+}
+
+bool can_segfuse(const mt_engine* e, const void* obs_in, const void* obs_out) {
+  int U, nc, window;
+  if (e->cfg.dtype == MT_F64) return segfused_geometry<double>(e, obs_in, obs_out, U, nc, window);
+  return segfused_geometry<float>(e, obs_in, obs_out, U, nc, window);
+}
+
+// steps fused per launch by mt_rollout on long roads (MT_SEGFUSE_STEPS: A/B knob)
+int segfuse_chunk() {
+  static int v = -1;
+  if (v < 0) {
+    const char* s = getenv("MT_SEGFUSE_STEPS");
+    v = s ? atoi(s) : 16;
+    if (v < 1) v = 1;
+    if (v > SEGFUSED_MAX_STEPS) v = SEGFUSED_MAX_STEPS;
+  }
+  return v;
+}
+
 // Steps roads [env0, env0 + n_env) of the batch; all pointers address the
 // whole batch (road 0) and are offset here.
 template <typename T>
@@ -973,6 +1111,25 @@ int mt_rollout(mt_engine* e, void* obs_a, void* obs_b, const void* actions, void
   }
   void* cur = obs_a;
   void* nxt = obs_b;
+  if (n_steps >= 2 && !rewards && can_segfuse(e, obs_a, obs_b)) {
+    // a road longer than one tile: overlapping windows of it advance by up to
+    // segfuse_chunk() steps per launch (mt_segfused.cuh)
+    if (e->params_pending) {
+      if ((cudaStream_t)stream != e->params_stream)
+        CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, e->params_ready, 0));
+      e->params_pending = false;
+    }
+    for (int done = 0; done < n_steps;) {
+      const int k = n_steps - done < segfuse_chunk() ? n_steps - done : segfuse_chunk();
+      const void* act = actions ? (const char*)actions + (size_t)done * stride : nullptr;
+      const int rc = segfused_any(e, cur, act, e->cfg.n_envs, nxt, k, nullptr, (cudaStream_t)stream);
+      if (rc != MT_OK) return rc;
+      void* tmp = cur; cur = nxt; nxt = tmp;
+      done += k;
+    }
+    if (result_in_b) *result_in_b = (cur == obs_b) ? 1 : 0;
+    return MT_OK;
+  }
   for (int s = 0; s < n_steps; ++s) {
     const void* act = actions ? (const char*)actions + (size_t)s * stride : nullptr;
     void* rew = rewards ? (char*)rewards + (size_t)s * stride : nullptr;
@@ -1300,6 +1457,51 @@ int mt_halo_pull(mt_halo* h, void* local, int64_t n_local, void* stream) {
   else
     halo_pull_kernel<float><<<1, 256, 0, (cudaStream_t)stream>>>(halo_args<float>(h, local, n_local, epoch));
   CUDA_TRY(cudaGetLastError());
+  return MT_OK;
+}
+
+int mt_halo_advance(mt_engine* e, mt_halo* h, void* obs_a, void* obs_b, int32_t n_steps,
+                    int32_t ghosts_fresh, void* stream, int32_t* result_in_b) {
+  if (!e || !h || !obs_a || !obs_b) return fail(MT_EINVAL, "mt_halo_advance: NULL argument");
+  if (!e->have_params) return fail(MT_ESTATE, "mt_halo_advance: call mt_set_params first");
+  if (obs_a == obs_b) return fail(MT_EINVAL, "mt_halo_advance: obs_a and obs_b must differ");
+  if (n_steps < 0) return fail(MT_EINVAL, "mt_halo_advance: n_steps must be >= 0");
+  if (e->cfg.n_envs != 1) return fail(MT_EINVAL, "mt_halo_advance: the engine must hold one road block");
+  if ((e->cfg.dtype == MT_F64) != (h->dtype == MT_F64) || e->cfg.device != h->device)
+    return fail(MT_EINVAL, "mt_halo_advance: engine and mailbox differ in dtype or device");
+  const int rc0 = halo_check(h, obs_a, e->cfg.n_cells, "mt_halo_advance");
+  if (rc0 != MT_OK) return rc0;
+  if (!can_segfuse(e, obs_a, obs_b))
+    return fail(MT_EINVAL, "mt_halo_advance: the block does not take the window kernel "
+                           "(too short, LOOP ends, or the direct-kernel flag)");
+  if ((h->left && e->params.bc_left != MT_BC_HALO) || (h->right && e->params.bc_right != MT_BC_HALO))
+    return fail(MT_EINVAL, "mt_halo_advance: an edge with a neighbour must have the MT_BC_HALO rule");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (e->params_pending) {
+    if (s != e->params_stream) CUDA_TRY(cudaStreamWaitEvent(s, e->params_ready, 0));
+    e->params_pending = false;
+  }
+  void* cur = obs_a;
+  void* nxt = obs_b;
+  bool fresh = ghosts_fresh != 0;
+  for (int done = 0; done < n_steps;) {
+    const int k = n_steps - done < h->halo ? n_steps - done : h->halo;
+    SegHalo hx;
+    hx.mine = h->box; hx.left = h->left; hx.right = h->right; hx.halo = h->halo;
+    hx.timeout_ns = 10ull * 1000ull * 1000ull * 1000ull;
+    if (!fresh) {
+      if (h->pulls >= h->pushes) return fail(MT_ESTATE, "mt_halo_advance: stale ghost cells and no push to pair with");
+      hx.pull_epoch = ++h->pulls;
+    }
+    hx.push_epoch = ++h->pushes;
+    const int rc = segfused_any(e, cur, nullptr, 0, nxt, k, &hx, s);
+    if (rc != MT_OK) return rc;
+    void* tmp = cur; cur = nxt; nxt = tmp;
+    done += k;
+    fresh = false;
+  }
+  if (result_in_b) *result_in_b = (cur == obs_b) ? 1 : 0;
   return MT_OK;
 }
 

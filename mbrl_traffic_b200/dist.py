@@ -65,6 +65,10 @@ class DomainDecomposedRoad(object):
         self.exchange = exchange or self._torch_exchange
         self.peer = None               # a PeerHalo: exchange over peer memory instead
         self._since_exchange = 0
+        self._push_pending = False     # the fused path has pushed; the ghosts await a pull
+        #: False keeps the exchange in its own push / pull launches even when the
+        #: fused path (PeerHalo.advance) applies -- for A/B measurements
+        self.fuse_exchange = True
 
     # ------------------------------------------------------------------ #
     def scatter(self, global_obs):
@@ -109,6 +113,9 @@ class DomainDecomposedRoad(object):
         bc_left, bc_right)`` (``engine_stepper`` does: one ``mt_rollout`` call,
         k back-to-back launches) each such run of steps is one call instead of
         k Python round trips."""
+        fused = self._fused_advance(local_obs, int(n_steps))
+        if fused is not None:
+            return fused
         block = getattr(self.stepper, "block", None)
         left = int(n_steps)
         while left > 0:
@@ -125,6 +132,31 @@ class DomainDecomposedRoad(object):
             self._since_exchange += k
             left -= k
         return local_obs
+
+    def _fused_advance(self, local_obs, n_steps):
+        """The whole run as ``mt_halo_advance`` launches (exchange folded into
+        the step kernel), or None when that path does not apply."""
+        engine = getattr(self.stepper, "engine", None)
+        buffers = getattr(self.stepper, "buffers", None)
+        if (self.peer is None or engine is None or buffers is None or n_steps < 1
+                or not self.fuse_exchange or not _is_torch(local_obs)):
+            return None
+        esz = local_obs.element_size()
+        if (self.halo * esz) % 16 or self.n_local % 4 or self.n_local <= 4096 // esz * 2:
+            return None      # (mt_halo_advance would refuse: short block or odd halo)
+        if not self._push_pending and 0 < self._since_exchange:
+            local_obs = self.refresh(local_obs)      # partly used ghosts: start from fresh ones
+        fresh = not self._push_pending
+        x, other = buffers(local_obs,
+                           "halo" if self.has_left else "physical",
+                           "halo" if self.has_right else "physical")
+        try:
+            out = self.peer.advance(engine, x, other, n_steps, fresh)
+        except ValueError:
+            return None
+        self._since_exchange = self.halo
+        self._push_pending = True
+        return out.reshape(local_obs.shape)
 
     def edge_cells(self, local_obs):
         """``(send_left, send_right)``: my first / last ``halo`` own cells as
@@ -155,7 +187,11 @@ class DomainDecomposedRoad(object):
     def refresh(self, local_obs):
         """Swap edge cells with the neighbours."""
         if self.peer is not None:      # peer-memory mailboxes: in place, on the GPU
-            self.peer.exchange(local_obs, self.n_local)
+            if self._push_pending:     # the fused path has already pushed this exchange
+                self.peer.pull(local_obs, self.n_local)
+                self._push_pending = False
+            else:
+                self.peer.exchange(local_obs, self.n_local)
             self._since_exchange = 0
             return local_obs
         send_l, send_r = self.edge_cells(local_obs)
@@ -266,6 +302,19 @@ class PeerHalo(object):
         self.push(local_obs, n_local, stream)
         self.pull(local_obs, n_local, stream)
 
+    def advance(self, engine, obs_a, obs_b, n_steps, ghosts_fresh, stream=None):
+        """``mt_halo_advance``: ``n_steps`` steps of the block with the exchange
+        folded into the step launches (one launch per ``halo`` steps).  Returns
+        the buffer that holds the final state; the ghost cells are stale and
+        one push is pending afterwards."""
+        import ctypes
+        from mbrl_traffic_b200.engine import _ptr, _stream_ptr
+        flag = ctypes.c_int32(0)
+        self._check(self._lib.mt_halo_advance(
+            engine._h, self._h, _ptr(obs_a), _ptr(obs_b), int(n_steps),
+            1 if ghosts_fresh else 0, _stream_ptr(stream), ctypes.byref(flag)))
+        return obs_b if flag.value else obs_a
+
     def timed_out(self):
         import ctypes
         flag = ctypes.c_int32(0)
@@ -352,4 +401,6 @@ def engine_stepper(engine, physical_left, physical_right, left_val=(0.0, 0.0),
 
     step.block = block
     step.physical = (physical_left, physical_right)
+    step.engine = engine
+    step.buffers = prepare
     return step
