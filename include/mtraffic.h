@@ -88,7 +88,7 @@ enum {
   MT_FLAG_NO_PIPELINE = 2,/* use the direct (one CTA per road tile) kernel
                              instead of the persistent TMA-pipelined one;
                              same results, for A/B measurements and tests  */
-  MT_FLAG_INDEPENDENT_INPUT = 4
+  MT_FLAG_INDEPENDENT_INPUT = 4,
                           /* the caller guarantees that the INPUT batch of a
                              step is not written by the work enqueued right
                              before it on the stream (independent batches, a
@@ -97,10 +97,22 @@ enum {
                              still drains; its stores still wait for it.
                              Same results.  Do NOT set it for chained steps
                              (input = the previous step's output).  Used only
-                             when this launch and the engine's previous one
+                             when this launch and the library's previous one
                              on the stream both fill the GPU (anything older
                              is then known to have finished), with scalar
-                             parameters and without speed limits / rewards. */
+                             parameters and without speed limits / rewards.
+                             WITHOUT this flag the library decides by itself:
+                             it remembers, per stream, the bytes its last
+                             launch writes and lets the next step's loads
+                             start early when its input lies outside them;
+                             a chained step (input = previous output) waits
+                             as before.                                    */
+  MT_FLAG_DEPENDENT_INPUT = 8
+                          /* every step waits for the launch before it
+                             (turns the automatic check above off; for A/B
+                             measurements, or when another library enqueues
+                             programmatic-dependent kernels that write this
+                             engine's inputs between its steps)            */
 };
 
 /* Fixed for the life of an engine. */

@@ -18,6 +18,7 @@ MT_BC_LOOP, MT_BC_EXTEND, MT_BC_CONSTANT, MT_BC_HALO = 0, 1, 2, 3
 MT_FLAG_FAST_MATH = 1
 MT_FLAG_NO_PIPELINE = 2
 MT_FLAG_INDEPENDENT_INPUT = 4
+MT_FLAG_DEPENDENT_INPUT = 8
 
 # every symbol include/mtraffic.h declares
 EXPORTS = (

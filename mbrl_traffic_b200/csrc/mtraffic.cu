@@ -27,6 +27,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 
 namespace {
@@ -164,10 +165,6 @@ struct mt_engine {
   // tile-schedule counters of the pipelined kernel: one {next, done} pair per
   // stream the engine launches on (slot 0: the caller's stream; 1..: hs[])
   unsigned int* sched = nullptr;
-  // MT_FLAG_INDEPENDENT_INPUT bookkeeping: stream of the previous launch when
-  // it was a pipelined step that filled every CTA slot of the GPU, else null
-  cudaStream_t last_full_pipe_stream = nullptr;
-  bool last_full_pipe = false;
   int max_tiles = 1;
   int sm_count = 148;
   bool have_params = false;
@@ -207,6 +204,50 @@ struct mt_halo {
 
 namespace {
 
+// ---------------------------------------------------------------------------
+// What this library enqueued LAST on a stream (process-wide: engines share
+// streams).  A pipelined step may start loading before the launch in front of
+// it has drained only if that launch is known and provably does not write what
+// this one reads; every other entry point that enqueues work forgets the
+// record, so "unknown" always means "wait".  (Work of other libraries between
+// two launches needs no record: an ordinary kernel or copy starts after the
+// launch before it has completed and is itself complete before a programmatic
+// dependent launch behind it starts.)
+// ---------------------------------------------------------------------------
+struct StreamNote {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  bool full_pipe = false;          // a single-step pipelined launch that filled every CTA slot
+  const char* out_lo = nullptr;    // bytes it writes: [out_lo, out_hi)
+  const char* out_hi = nullptr;
+};
+constexpr int MAX_NOTES = 32;
+std::mutex g_note_mu;
+StreamNote g_notes[MAX_NOTES];
+int g_note_next = 0;
+
+// returns the record of (device, stream) and forgets it
+StreamNote note_take(int device, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(g_note_mu);
+  for (int i = 0; i < MAX_NOTES; ++i) {
+    StreamNote& n = g_notes[i];
+    if (n.device == device && n.stream == stream) {
+      const StreamNote out = n;
+      n = StreamNote();
+      return out;
+    }
+  }
+  return StreamNote();
+}
+void note_put(const StreamNote& note) {
+  std::lock_guard<std::mutex> lock(g_note_mu);
+  for (int i = 0; i < MAX_NOTES; ++i)
+    if (g_notes[i].device < 0) { g_notes[i] = note; return; }
+  g_notes[g_note_next] = note;     // table full: overwrite round-robin (forgetting is safe)
+  g_note_next = (g_note_next + 1) % MAX_NOTES;
+}
+inline void note_forget(int device, void* stream) { (void)note_take(device, (cudaStream_t)stream); }
+
 struct Geometry {
   bool vector_ok;
   int nvec, tpe, epc, tiles, block;
@@ -240,6 +281,16 @@ bool pipe_use_pdl() {
   static int v = -1;
   if (v < 0) {
     const char* s = getenv("MT_PDL");
+    v = (s && s[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+// the automatic independent-input check (MT_AUTO_INDEPENDENT=0 disables: A/B knob)
+bool auto_independent() {
+  static int v = -1;
+  if (v < 0) {
+    const char* s = getenv("MT_AUTO_INDEPENDENT");
     v = (s && s[0] == '0') ? 0 : 1;
   }
   return v != 0;
@@ -654,6 +705,7 @@ int segfused_typed(mt_engine* e, const void* obs_in_, const void* action_, long 
 
 int segfused_any(mt_engine* e, const void* obs_in, const void* action, long long action_stride,
                  void* obs_out, int n_inner, const SegHalo* hx, cudaStream_t stream) {
+  note_forget(e->cfg.device, stream);
   if (e->cfg.dtype == MT_F64)
     return segfused_typed<double>(e, obs_in, action, action_stride, obs_out, n_inner, hx, stream);
   return segfused_typed<float>(e, obs_in, action, action_stride, obs_out, n_inner, hx, stream);
@@ -684,8 +736,7 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
                void* reward_out_, long long env0, long long n_env, cudaStream_t stream,
                int n_inner = 1, long long action_stride = -1, long long reward_stride = 0) {
   // (see the early-load bookkeeping in the pipelined branch)
-  const bool prev_full_pipe = e->last_full_pipe;
-  e->last_full_pipe = false;
+  const StreamNote prev = note_take(e->cfg.device, stream);
   constexpr int V = Vec<T>::N;
   const mt_params& p = e->params;
   const long long B = n_env;
@@ -771,21 +822,34 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
         if (e->hs[j] != nullptr && stream == e->hs[j]) slot = j + 1;
       pa.sched = e->sched + 2 * slot;
     }
-    // Early loads (MT_FLAG_INDEPENDENT_INPUT).  The caller vouches for the launch
-    // right before this one; older launches must be finished on their own
-    // account, which holds when that launch AND this one fill every CTA slot: a
+    // Early loads: the producer issues its first ring-full of loads BEFORE it
+    // waits for the launch in front of it, so this launch's pipeline fills
+    // while that one drains (stores still wait).  Allowed when that launch is
+    // on record (note_take above), filled every CTA slot like this one -- a
     // CTA of this launch then only finds room once a CTA of the previous launch
     // has exited, i.e. after the previous launch has itself waited for
-    // everything before it.  Consumers must not touch global memory before the
-    // wait: scalar parameters, no speed limits, no rewards.
+    // everything before it -- and writes nothing this launch reads: checked
+    // here on the byte ranges, or vouched for by the caller
+    // (MT_FLAG_INDEPENDENT_INPUT).  MT_FLAG_DEPENDENT_INPUT turns the check
+    // off: every launch waits.  Consumers must not touch global memory before
+    // the wait: scalar parameters, no speed limits, no rewards.
     const bool full_grid = (long long)grid == slots;
-    pa.early_loads = ((p.flags & MT_FLAG_INDEPENDENT_INPUT) && e->uniform && action == nullptr &&
-                      reward_out == nullptr && n_inner == 1 && pipe_use_pdl() && full_grid &&
-                      prev_full_pipe && e->last_full_pipe_stream == stream) ? 1 : 0;
-    e->last_full_pipe = full_grid && n_inner == 1 &&
-                        !pipe_use_ring(sizeof(T) == 4, fast, e->cfg.model == MT_MODEL_ARZ,
+    const char* in_lo = (const char*)obs_in;
+    const char* in_hi = in_lo + (size_t)B * 2 * N * sizeof(T);
+    const bool disjoint = prev.out_hi <= in_lo || in_hi <= prev.out_lo;
+    const bool independent = (p.flags & MT_FLAG_INDEPENDENT_INPUT) ||
+                             (!(p.flags & MT_FLAG_DEPENDENT_INPUT) && auto_independent() && disjoint);
+    const bool is_ring = pipe_use_ring(sizeof(T) == 4, fast, e->cfg.model == MT_MODEL_ARZ,
                                        pa.sched != nullptr);
-    e->last_full_pipe_stream = stream;
+    pa.early_loads = (independent && e->uniform && action == nullptr && reward_out == nullptr &&
+                      n_inner == 1 && pipe_use_pdl() && full_grid && !is_ring &&
+                      prev.full_pipe) ? 1 : 0;
+    StreamNote mine;
+    mine.device = e->cfg.device;
+    mine.stream = stream;
+    mine.full_pipe = full_grid && n_inner == 1 && !is_ring && pipe_use_pdl();
+    mine.out_lo = (const char*)obs_out;
+    mine.out_hi = mine.out_lo + (size_t)B * 2 * N * sizeof(T);
     int rc;
     if (e->cfg.model == MT_MODEL_ARZ)
       rc = U == 2 ? launch_pipe_model<T, 1, 2>(pa, grid, fast, e->uniform, e->lamk, stream)
@@ -796,6 +860,7 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
     if (rc != MT_OK) return rc;
     e->launches++;
     CUDA_TRY(cudaGetLastError());
+    note_put(mine);
     return MT_OK;
   }
 
@@ -1058,7 +1123,7 @@ int mt_set_params(mt_engine* e, const mt_params* p, void* stream) {
                        (const float*)p->rho_crit_env};
     set_params_kernel<float><<<grid, block, 0, s>>>(a);
   }
-  e->last_full_pipe = false;
+  note_forget(e->cfg.device, s);
   e->launches++;
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(e->params_ready, s));
@@ -1257,6 +1322,7 @@ int mt_density_sqerr(mt_engine* e, const void* obs_pred, const void* obs_target,
   else
     density_sqerr_kernel<float><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(
         (const float*)obs_pred, (const float*)obs_target, (float*)out_per_env, B, N);
+  note_forget(e->cfg.device, stream);
   e->launches++;
   CUDA_TRY(cudaGetLastError());
   return MT_OK;
@@ -1274,7 +1340,7 @@ int mt_nonfinite(mt_engine* e, const void* obs, int32_t* flags_out, void* stream
   else
     nonfinite_kernel<float><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const float*)obs,
                                                                          flags_out, B, N);
-  e->last_full_pipe = false;
+  note_forget(e->cfg.device, stream);
   e->launches++;
   CUDA_TRY(cudaGetLastError());
   return MT_OK;

@@ -84,6 +84,22 @@ class DomainDecomposedRoad(object):
             return torch.cat((rho, v)).contiguous()
         return np.concatenate((rho, v))
 
+    def begin(self, global_obs):
+        """``scatter`` for a NEW run on this object: besides cutting the block
+        out it forgets the previous run's exchange state.  A run that ended on
+        the fused path leaves one push in the mailboxes (its ghost cells were
+        never pulled); that push is consumed here, so that the first launch of
+        the new run uses the fresh ghosts it was handed instead of pulling the
+        old run's edge cells.  Every rank must call it."""
+        x = self.scatter(global_obs)
+        if _is_torch(x):
+            x = x.clone()
+        if self._push_pending:
+            self.peer.pull(x.clone(), self.n_local)     # (result discarded)
+            self._push_pending = False
+        self._since_exchange = 0
+        return x
+
     def own(self, local_obs):
         """The cells this rank owns (ghosts stripped) as ``(rho, v)``."""
         x = local_obs.reshape(-1)

@@ -126,7 +126,8 @@ class Engine(object):
     # ------------------------------------------------------------------ #
     def set_params(self, dx, dt, rho_max, v_max, lam, boundary_conditions,
                    tau=1.0, rho_crit=None, gamma=None, fast_math=False,
-                   no_pipeline=False, independent_input=False, stream=None):
+                   no_pipeline=False, independent_input=False, dependent_input=False,
+                   stream=None):
         """``mt_set_params``.  rho_max / v_max / tau / lam / rho_crit may be
         Python scalars or device tensors of shape (n_envs,) in the engine
         dtype; ``gamma`` is a device tensor of look-ahead weights."""
@@ -167,7 +168,8 @@ class Engine(object):
             p.n_eta = int(gamma.numel())
         p.flags = (_lib.MT_FLAG_FAST_MATH if fast_math else 0) | \
             (_lib.MT_FLAG_NO_PIPELINE if no_pipeline else 0) | \
-            (_lib.MT_FLAG_INDEPENDENT_INPUT if independent_input else 0)
+            (_lib.MT_FLAG_INDEPENDENT_INPUT if independent_input else 0) | \
+            (_lib.MT_FLAG_DEPENDENT_INPUT if dependent_input else 0)
         _lib.check(self._lib.mt_set_params(self._h, ctypes.byref(p),
                                            _stream_ptr(stream)))
         self._keep = keep

@@ -39,21 +39,24 @@ def ref_step(kind, obs, steps=1):
     return out
 
 
-def engine(kind="arz", b=B, n=N, independent=False):
+def engine(kind="arz", b=B, n=N, mode="auto"):
+    """mode: "auto" (the library checks the byte ranges itself), "vouched"
+    (MT_FLAG_INDEPENDENT_INPUT) or "dependent" (MT_FLAG_DEPENDENT_INPUT)."""
     from mbrl_traffic_b200.engine import Engine
     eng = Engine(kind, "float64", b, n)
-    eng.set_params(independent_input=independent, **PARAMS)
+    eng.set_params(independent_input=(mode == "vouched"),
+                   dependent_input=(mode == "dependent"), **PARAMS)
     return eng
 
 
-@pytest.mark.parametrize("independent", [False, True])
+@pytest.mark.parametrize("mode", ["auto", "vouched", "dependent"])
 @pytest.mark.parametrize("kind", ["arz", "lwr"])
-def test_pool_of_batches_eager_and_graph_bit_exact(kind, independent):
+def test_pool_of_batches_eager_and_graph_bit_exact(kind, mode):
     """A pool of four full-GPU batches stepped round-robin, eagerly and from a
-    replayed CUDA graph (with and without MT_FLAG_INDEPENDENT_INPUT): every
-    output equals the oracle's."""
+    replayed CUDA graph, with the early loads decided by the library, vouched
+    for by the caller, or switched off: every output equals the oracle's."""
     _need_gpu()
-    eng = engine(kind, independent=independent)
+    eng = engine(kind, mode=mode)
     obs = [make_obs(j) for j in range(4)]
     ins = [torch.as_tensor(x, device="cuda:0") for x in obs]
     outs = [torch.zeros_like(x) for x in ins]

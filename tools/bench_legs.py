@@ -234,13 +234,11 @@ def leg_long_road(ctx, args):
     d.stepper = engine_stepper(eng, _lib.MT_BC_EXTEND, _lib.MT_BC_EXTEND, **params)
     peer = PeerHalo(halo, "float64", ctx.local_rank).connect_group(ctx.rank, ctx.world)
     d.peer = peer
-    x = d.scatter(road).clone()
-    d._since_exchange = 0
+    x = d.begin(road)
     d.advance(x, 2 * halo)                  # warm-up incl. two exchanges
     times = []
     for _ in range(3):
-        x = d.scatter(road).clone()
-        d._since_exchange = 0
+        x = d.begin(road)                   # (consumes the previous run's pending push)
         ctx.barrier()
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
