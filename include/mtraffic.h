@@ -80,6 +80,14 @@ typedef enum mt_bc {
   MT_BC_HALO = 3
 } mt_bc;
 
+/* Numerical scheme of the non-local model (the reference only names the
+ * model, utils/train.py:685-689; lwr.py:209-211 cites the first paper):
+ *   GODUNOV  mean downstream VELOCITY, upwind flux rho_j W_j
+ *            (Friedrich, Kolb, Goettlich, NHM 13, 2018)
+ *   LXF      speed of the mean downstream DENSITY, Lax-Friedrichs flux
+ *            (Blandin, Goatin, Numer. Math. 132, 2016)                      */
+typedef enum { MT_SCHEME_GODUNOV = 0, MT_SCHEME_LXF = 1 } mt_scheme;
+
 enum {
   /* mt_params.flags */
   MT_FLAG_FAST_MATH = 1,  /* allow FMA contraction, approximate division and
@@ -144,6 +152,10 @@ typedef struct mt_params {
   const void *gamma;          /* non-local: DEVICE array of n_eta weights    */
   int32_t n_eta;
   int32_t flags;
+  int32_t scheme;             /* non-local: mt_scheme                        */
+  int32_t reserved;
+  double alpha;               /* non-local, MT_SCHEME_LXF: numerical viscosity
+                                 (>= max |V|); < 0 means each road's v_max   */
 } mt_params;
 
 int mt_version(void);

@@ -15,6 +15,7 @@ MT_OK, MT_EINVAL, MT_ECUDA, MT_ENOMEM, MT_ESTATE = 0, -1, -2, -3, -4
 MT_MODEL_LWR, MT_MODEL_ARZ, MT_MODEL_NONLOCAL = 0, 1, 2
 MT_F32, MT_F64 = 0, 1
 MT_BC_LOOP, MT_BC_EXTEND, MT_BC_CONSTANT, MT_BC_HALO = 0, 1, 2, 3
+MT_SCHEME_GODUNOV, MT_SCHEME_LXF = 0, 1
 MT_FLAG_FAST_MATH = 1
 MT_FLAG_NO_PIPELINE = 2
 MT_FLAG_INDEPENDENT_INPUT = 4
@@ -54,6 +55,8 @@ class MtParams(ctypes.Structure):
         ("bc_right_val", ctypes.c_double * 2),
         ("gamma", ctypes.c_void_p),
         ("n_eta", ctypes.c_int32), ("flags", ctypes.c_int32),
+        ("scheme", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("alpha", ctypes.c_double),
     ]
 
 

@@ -22,6 +22,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
     "-Xcompiler", "-fPIC", "-shared",
+    # one translation unit, ~290 kernels: let ptxas work on them in parallel
+    "-split-compile", str(max(1, min(8, os.cpu_count() or 1))),
     "-I", os.path.join(ROOT, "include"),
 ]
 

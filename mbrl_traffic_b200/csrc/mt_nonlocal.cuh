@@ -9,7 +9,21 @@
 //     rho'_j    = rho_j - (dt/dx) (F_{j+1/2} - F_{j-1/2}),   v'_j = V(rho'_j)
 //
 // exactly as oracle/np_oracle.py nonlocal_step evaluates it (same operation
-// order, no FMA in EXACT mode).  Ghost cells: one upstream, n_eta downstream;
+// order, no FMA in EXACT mode).
+//
+// Second scheme (LXF = true; mt_params.scheme = MT_SCHEME_LXF): the model of
+// Blandin & Goatin, Numer. Math. 132 (2016), whose speed depends on a mean of
+// the downstream DENSITIES, with a Lax-Friedrichs flux:
+//
+//     R_j       = sum_{k=0}^{n_eta-1} gamma_k rho_{j+k}          (k ascending)
+//     g_j       = rho_j V(R_j)
+//     F_{j+1/2} = 0.5 (g_j + g_{j+1}) + (alpha/2) (rho_j - rho_{j+1})
+//     rho'_j    = rho_j - (dt/dx) (F_{j+1/2} - F_{j-1/2})
+//
+// as oracle/np_oracle.py nonlocal_lxf_step evaluates it.  Same kernel: the
+// shared array then holds the densities themselves, shifted by one slot (slot
+// 0 = the upstream ghost), and a thread accumulates R for its cells and BOTH
+// neighbours (CPT + 2 windows instead of CPT + 1).  Ghost cells: one upstream, n_eta downstream;
 // LOOP = periodic ring, EXTEND = copy of the edge cell, CONSTANT = given value.
 //
 // Pipelined kernel: same producer/consumer skeleton as mt_pipe.cuh, but only
@@ -64,6 +78,7 @@ template <typename T> struct NlArgs {
   int ve_cols;     // columns per plane of a road's V(rho) block: nthr + ghost columns
   BcArgs<T> bc;
   T step;
+  T half_alpha;    // LXF: alpha / 2, or < 0: half of each road's v_max
   UniformC<T> u;
 };
 
@@ -75,10 +90,11 @@ __device__ __forceinline__ T nl_left_ghost(const BcArgs<T>& b, const T* rho_row,
   return rho_row[0];
 }
 
-template <typename T, bool FAST, int LAMK, bool UNIFORM, int U>
+template <typename T, bool FAST, int LAMK, bool UNIFORM, int U, bool LXF>
 __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) nonlocal_pipe_kernel(const NlArgs<T> a) {
   constexpr int V = Vec<T>::N;
   constexpr int CPT = U * V;
+  constexpr int ACC = LXF ? CPT + 2 : CPT + 1;     // look-ahead sums per thread
   using A = Ar<T, FAST>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   NlSmem<T>& sm = *reinterpret_cast<NlSmem<T>*>(smem_raw);
@@ -193,6 +209,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) nonlocal_pipe_kernel(c
 #pragma unroll
         for (int k = 0; k < V; ++k) rho[u * V + k] = tmp[k];
       }
+      if constexpr (!LXF) {
       T ghost_v = T(0);   // V(rho_R) for a CONSTANT downstream end
       with_lam<LAMK>(e.flags, [&](auto kind) {
         constexpr int K = decltype(kind)::value;
@@ -214,6 +231,25 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) nonlocal_pipe_kernel(c
         for (int c = 0; c < n_eta; ++c) blk[(c % CPT) * VSTR + a.nthr + c / CPT] = g;
       }
       rho_left = row_first ? nl_left_ghost(a.bc, rho_row, N) : rho_row[j0 - 1];
+      } else {
+      // LXF: the densities themselves, cell c in slot c + 1 (slot 0 = upstream
+      // ghost): my cell j0 + k sits in plane (k + 1) mod CPT, column pos (+ 1
+      // for my last cell)
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) {
+        const int idx = ve_row + (k < CPT - 1 ? (k + 1) * VSTR : 1);
+        ve[idx] = rho[k];
+        // ring: cell c < n_eta is also the downstream ghost N + c
+        if (a.bc.bc_r == MT_BC_LOOP && j0 + k < n_eta) ve[idx + a.nthr] = rho[k];
+      }
+      if (row_first) ve[el * (CPT * VSTR)] = nl_left_ghost(a.bc, rho_row, N);
+      if (row_last && a.bc.bc_r != MT_BC_LOOP) {
+        const T g = (a.bc.bc_r == MT_BC_CONSTANT) ? a.bc.br0 : rho[CPT - 1];
+        T* blk = ve + el * (CPT * VSTR);
+        for (int c = 1; c <= n_eta; ++c) blk[(c % CPT) * VSTR + a.nthr + c / CPT] = g;
+      }
+      (void)mine;
+      }
     }
     consumer_sync(NC);                               // V(rho) published; stage s read
     if (lane0) mbar_arrive(empty0 + 8 * s);
@@ -221,32 +257,59 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) nonlocal_pipe_kernel(c
 
     T num = 0, den = 0;
     if (active) {
-      // W for cells j0-1 .. j0+CPT-1: acc[m] covers cell j0-1+m and needs
-      // ve[j0+m+k], k < n_eta.  A register window slides by one per k.
-      T acc[CPT + 1], win[CPT + 1];
-      const T* vcol = ve + ve_row;                   // cell j0 + x: plane x % CPT, column + x / CPT
+      // Godunov: W for cells j0-1 .. j0+CPT-1: acc[m] covers cell j0-1+m and
+      // needs ve[j0+m+k], k < n_eta.  LXF: R for cells j0-1 .. j0+CPT: acc[m]
+      // covers cell j0-1+m and needs slot j0+m+k.  Either way thread-relative
+      // index m + k: a register window slides by one per k.
+      T acc[ACC], win[ACC];
+      const T* vcol = ve + ve_row;                   // index x: plane x % CPT, column + x / CPT
 #pragma unroll
-      for (int m = 0; m <= CPT; ++m) {
+      for (int m = 0; m < ACC; ++m) {
         acc[m] = T(0);
         win[m] = vcol[(m % CPT) * VSTR + m / CPT];
       }
+      // LXF: the window's first and last entry are the two neighbour cells
+      const T cell_l = win[0], cell_r = win[ACC - 1];
       for (int k = 0; k < n_eta; ++k) {
         const T g = sm.gamma[k];
-        const int x = k + CPT + 1;
+        const int x = k + ACC;
         const T nxt = vcol[(x % CPT) * VSTR + x / CPT];
 #pragma unroll
-        for (int m = 0; m <= CPT; ++m) acc[m] = A::mad(g, win[m], acc[m]);  // w + gamma_k * V
+        for (int m = 0; m < ACC; ++m) acc[m] = A::mad(g, win[m], acc[m]);  // w + gamma_k * V
 #pragma unroll
-        for (int m = 0; m < CPT; ++m) win[m] = win[m + 1];
-        win[CPT] = nxt;
+        for (int m = 0; m < ACC - 1; ++m) win[m] = win[m + 1];
+        win[ACC - 1] = nxt;
       }
       T rn[CPT], vn[CPT];
-      T Fm = A::mul(rho_left, acc[0]);               // F_{j0-1/2}
+      if constexpr (!LXF) {
+        T Fm = A::mul(rho_left, acc[0]);               // F_{j0-1/2}
 #pragma unroll
-      for (int k = 0; k < CPT; ++k) {
-        const T F = A::mul(rho[k], acc[k + 1]);
-        rn[k] = A::sub(rho[k], A::mul(e.step, A::sub(F, Fm)));
-        Fm = F;
+        for (int k = 0; k < CPT; ++k) {
+          const T F = A::mul(rho[k], acc[k + 1]);
+          rn[k] = A::sub(rho[k], A::mul(e.step, A::sub(F, Fm)));
+          Fm = F;
+        }
+        (void)cell_l; (void)cell_r;
+      } else {
+        T c[CPT + 2], gq[CPT + 2];
+        c[0] = cell_l;
+        c[CPT + 1] = cell_r;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) c[k + 1] = rho[k];
+        with_lam<LAMK>(e.flags, [&](auto kind) {
+          constexpr int K = decltype(kind)::value;
+#pragma unroll
+          for (int m = 0; m < CPT + 2; ++m) gq[m] = A::mul(c[m], v_eq<T, FAST, K>(acc[m], e));
+        });
+        const T ha = a.half_alpha < T(0) ? A::mul(T(0.5), e.v_max) : a.half_alpha;
+        T Fm = A::add(A::mul(T(0.5), A::add(gq[0], gq[1])), A::mul(ha, A::sub(c[0], c[1])));
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+          const T F = A::add(A::mul(T(0.5), A::add(gq[k + 1], gq[k + 2])),
+                             A::mul(ha, A::sub(c[k + 1], c[k + 2])));
+          rn[k] = A::sub(rho[k], A::mul(e.step, A::sub(F, Fm)));
+          Fm = F;
+        }
       }
       with_lam<LAMK>(e.flags, [&](auto kind) {
         constexpr int K = decltype(kind)::value;
@@ -325,7 +388,42 @@ template <typename T> struct NlScalarArgs {
   int N;
   BcArgs<T> bc;
   T step;
+  T half_alpha;
 };
+
+// LXF scheme, one thread per cell (see the header comment)
+template <typename T, bool FAST>
+__global__ void nonlocal_lxf_scalar_kernel(const NlScalarArgs<T> a) {
+  using A = Ar<T, FAST>;
+  constexpr int LAMK = LAM_RUNTIME;
+  const int N = a.N;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= a.B * N) return;
+  const long long env = gid / N;
+  const int j = (int)(gid - env * N);
+  EnvC<T> e;
+  load_env(e, a.table, a.flags, env, a.action, a.step);
+  const T* row = a.in + env * (2LL * N);
+  T r[3] = {T(0), T(0), T(0)};       // R of cells j-1, j, j+1
+  for (int k = 0; k < a.n_eta; ++k) {
+    const T g = a.gamma[k];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) r[m] = A::mad(g, nl_rho_at(a.bc, row, N, j - 1 + m + k), r[m]);
+  }
+  T c[3], gq[3];
+#pragma unroll
+  for (int m = 0; m < 3; ++m) {
+    c[m] = nl_rho_at(a.bc, row, N, j - 1 + m);
+    gq[m] = A::mul(c[m], v_eq<T, FAST, LAMK>(r[m], e));
+  }
+  const T ha = a.half_alpha < T(0) ? A::mul(T(0.5), e.v_max) : a.half_alpha;
+  const T Fm = A::add(A::mul(T(0.5), A::add(gq[0], gq[1])), A::mul(ha, A::sub(c[0], c[1])));
+  const T F = A::add(A::mul(T(0.5), A::add(gq[1], gq[2])), A::mul(ha, A::sub(c[1], c[2])));
+  const T rn = A::sub(c[1], A::mul(e.step, A::sub(F, Fm)));
+  T* orow = a.out + env * (2LL * N);
+  orow[j] = rn;
+  orow[N + j] = v_eq<T, FAST, LAMK>(rn, e);
+}
 
 template <typename T, bool FAST>
 __global__ void nonlocal_scalar_kernel(const NlScalarArgs<T> a) {

@@ -232,6 +232,7 @@ static_assert(sizeof(PipeSmem<double, 2>) <= (228 / PIPE_CTAS - 1) * 1024, "f64 
 static_assert(sizeof(PipeSmem<float, 2>) <= (228 / PIPE_CTAS - 1) * 1024, "f32 U=2 smem");
 static_assert(PIPE_CTAS >= 3 || sizeof(PipeSmem<double, 1>) <= 113 * 1024, "f64 U=1 smem");
 static_assert(PIPE_CTAS >= 3 || sizeof(PipeSmem<float, 1>) <= 113 * 1024, "f32 U=1 smem");
+static_assert(PIPE_OUT <= 2, "r_num / r_den hold one set of warp sums per output stage");
 
 #ifdef MT_TRACE
 // experimental build only (tools/trace_pipe.py): per-CTA %globaltimer stamps
@@ -281,6 +282,11 @@ template <typename T> struct PipeArgs {
   int early_loads = 0;
   int early_l2 = 2;  // tiles per CTA pulled towards L2 before the grid-dependency wait
   int l2_hint = 0;   // != 0: tile loads carry L2::evict_first (a tile is read once per step)
+  // Per-road parameter tables (the non-UNIFORM instantiations): byte offset
+  // inside an input stage at which the producer places the tile's table rows
+  // (they fit behind the roads: the host picks epc accordingly); 0: the
+  // consumers read their rows from global memory instead.
+  int tbl_off = 0;
 };
 
 // Which instantiations of step_pipe_kernel draw their tiles from a counter.
@@ -388,26 +394,55 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
         if (hint_ld) bulk_load_hint(dst, src, bytes, bar, pol_ld);
         else bulk_load(dst, src, bytes, bar);
       };
+      // the tile's rows of the per-road parameter table travel with it (no
+      // eviction hint: the table is read again by every step)
+      constexpr uint32_t TBL_ROW_BYTES = TBL_STRIDE * (uint32_t)sizeof(T);
+      auto tbl_bytes_of = [&](int envs) -> uint32_t {
+        return (!UNIFORM && a.tbl_off != 0) ? (uint32_t)envs * TBL_ROW_BYTES : 0u;
+      };
+      auto table_load = [&](int s, int tile, uint32_t bytes) {
+        if (bytes != 0)
+          bulk_load(in0 + (uint32_t)s * PIPE_TILE_BYTES + (uint32_t)a.tbl_off,
+                    reinterpret_cast<const unsigned char*>(a.table) +
+                        (size_t)tile * a.epc * TBL_ROW_BYTES,
+                    bytes, full0 + 8 * s);
+      };
+      // Rewards of roads wider than a warp: the consumer warps leave their
+      // partial sums next to the finished tile (r_num / r_den[o]); this thread
+      // adds them up in warp order and stores the quotient, so the consumers
+      // need no second barrier per tile.
+      auto finish_rewards = [&](int o, int tile) {
+        if (a.reward == nullptr || a.tpe <= 32) return;
+        const int envs = tile == last_tile ? last_envs : a.epc;
+        const int nw = a.tpe >> 5;
+        for (int el = 0; el < envs; ++el) {
+          T n = sm.r_num[o][el * nw], d = sm.r_den[o][el * nw];
+          for (int j = 1; j < nw; ++j) { n += sm.r_num[o][el * nw + j]; d += sm.r_den[o][el * nw + j]; }
+          a.reward[(size_t)tile * a.epc + el] = n / d;
+        }
+      };
       if constexpr (!DYN) {
         auto issue_load = [&](int i) {
           const int tile = (int)blockIdx.x + i * (int)gridDim.x;
           const int s = i % PIPE_STAGES;
+          const int envs = tile == last_tile ? last_envs : a.epc;
+          const uint32_t tbl = tbl_bytes_of(envs);
           if (ARZ) {
             const uint32_t bytes = bytes_of(tile);
-            mbar_expect_tx(full0 + 8 * s, bytes);
+            mbar_expect_tx(full0 + 8 * s, bytes + tbl);
             tile_load(in0 + (uint32_t)s * PIPE_TILE_BYTES, gin + (size_t)tile * tile_bytes, bytes,
                       full0 + 8 * s);
           } else {
             // LWR ignores the input velocity (lwr.py:197): fetch the density half
             // of each road only, at its usual place in the stage
-            const int envs = tile == last_tile ? last_envs : a.epc;
             const uint32_t half = row_bytes >> 1;
-            mbar_expect_tx(full0 + 8 * s, (uint32_t)envs * half);
+            mbar_expect_tx(full0 + 8 * s, (uint32_t)envs * half + tbl);
             for (int r = 0; r < envs; ++r)
               tile_load(in0 + (uint32_t)s * PIPE_TILE_BYTES + (uint32_t)r * row_bytes,
                         gin + (size_t)tile * tile_bytes + (size_t)r * row_bytes, half,
                         full0 + 8 * s);
           }
+          table_load(s, tile, tbl);
         };
         auto prefetch = [&](int i) {
           const int tile = (int)blockIdx.x + i * (int)gridDim.x;
@@ -437,6 +472,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
           bulk_store(gout + (size_t)tile * tile_bytes, out0 + (uint32_t)o * PIPE_TILE_BYTES,
                      bytes_of(tile));
           bulk_commit();
+          finish_rewards(o, tile);
           // all but the newest PIPE_OUT-1 stores have finished reading shared memory
           bulk_wait_read<PIPE_OUT - 1>();
           if (i >= PIPE_OUT - 1) mbar_arrive(ofree0 + 8 * ((i - (PIPE_OUT - 1)) % PIPE_OUT));
@@ -464,22 +500,24 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
             mbar_arrive(full0 + 8 * s);
             return;
           }
+          const int envs = tile == last_tile ? last_envs : a.epc;
+          const uint32_t tbl = tbl_bytes_of(envs);
           if (ARZ) {
             const uint32_t bytes = bytes_of(tile);
-            mbar_expect_tx(full0 + 8 * s, bytes);
+            mbar_expect_tx(full0 + 8 * s, bytes + tbl);
             tile_load(in0 + (uint32_t)s * PIPE_TILE_BYTES, gin + (size_t)tile * tile_bytes, bytes,
                       full0 + 8 * s);
           } else {
             // LWR ignores the input velocity (lwr.py:197): fetch the density half
             // of each road only, at its usual place in the stage
-            const int envs = tile == last_tile ? last_envs : a.epc;
             const uint32_t half = row_bytes >> 1;
-            mbar_expect_tx(full0 + 8 * s, (uint32_t)envs * half);
+            mbar_expect_tx(full0 + 8 * s, (uint32_t)envs * half + tbl);
             for (int r = 0; r < envs; ++r)
               tile_load(in0 + (uint32_t)s * PIPE_TILE_BYTES + (uint32_t)r * row_bytes,
                         gin + (size_t)tile * tile_bytes + (size_t)r * row_bytes, half,
                         full0 + 8 * s);
           }
+          table_load(s, tile, tbl);
         };
         auto prefetch = [&](int tile) {
           if (tile < 0) return;
@@ -516,6 +554,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
           bulk_store(gout + (size_t)tile * tile_bytes, out0 + (uint32_t)o * PIPE_TILE_BYTES,
                      bytes_of(tile));
           bulk_commit();
+          finish_rewards(o, tile);
           // all but the newest PIPE_OUT-1 stores have finished reading shared memory
           bulk_wait_read<PIPE_OUT - 1>();
           if (i >= PIPE_OUT - 1) mbar_arrive(ofree0 + 8 * ((i - (PIPE_OUT - 1)) % PIPE_OUT));
@@ -579,7 +618,8 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
     const int env = tile * a.epc + el;
     const bool active = owns_cells && (el < envs_here);
 
-    if (active && (!UNIFORM || a.action != nullptr)) {
+    const bool staged_table = !UNIFORM && a.tbl_off != 0;
+    if (active && !staged_table && (!UNIFORM || a.action != nullptr)) {
       // per-road constants (and/or this step's speed limit); with the static
       // schedule they are issued before the wait so that the loads overlap it
       if (UNIFORM) load_uniform(e, a.u, env, a.action, a.step);
@@ -588,6 +628,14 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
     }
 
     if constexpr (!DYN) mbar_wait(full0 + 8 * s, ph_in);
+    if constexpr (!UNIFORM) {
+      if (active && staged_table) {
+        // my road's row of the parameter table arrived with the tile
+        const T* trow = reinterpret_cast<const T*>(sm.in[s] + a.tbl_off) + el * TBL_STRIDE;
+        load_env_staged(e, trow, env, a.action, a.step);
+        if (ARZ) e.qc = A::mul(e.rho_crit, A::mul(e.v_max, e.g_crit));
+      }
+    }
 
     if (t == 0) { if (i == 0) MT_STAMP(2); MT_STAMP(4); }
     T rho[CPT], v[CPT], y[CPT], r[CPT], D[CPT], S[CPT];
@@ -660,41 +708,34 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
         sts16(dst + v_off + 16 * u, tv);
       }
     }
+    if (want_reward && a.tpe > 32) {
+      // Per-road sum(rho v) / sum(rho), fixed order.  Shuffles are the cost of
+      // this reduction (one warp-wide SHFL per clock and SM), so the two sums
+      // share one butterfly: in the first round even lanes keep the numerator
+      // and odd lanes the denominator of the pair, the other four rounds then
+      // move ONE value per lane.  Lane 0 ends up with the warp's numerator,
+      // lane 1 with its denominator; they go next to the finished tile and
+      // the producer thread adds the warps up (finish_rewards).
+      const unsigned full = 0xffffffffu;
+      const bool odd = (t & 1) != 0;
+      T acc = (odd ? den : num) + __shfl_xor_sync(full, odd ? num : den, 1);
+      for (int off = 2; off <= 16; off <<= 1) acc += __shfl_xor_sync(full, acc, off);
+      if ((t & 31) == 0) sm.r_num[o][t >> 5] = acc;
+      if ((t & 31) == 1) sm.r_den[o][t >> 5] = acc;
+    }
     fence_proxy_async_smem();  // my generic-proxy writes -> visible to the bulk engine
     __syncwarp();
     if (lane0) mbar_arrive(ofull0 + 8 * o);          // non-blocking hand-off to the producer
     if (t == 0) MT_STAMP(5);
 
-    if (want_reward) {
-      // per-road sum(rho v)/sum(rho) in a fixed order
+    if (want_reward && a.tpe <= 32) {
+      // a road fits one warp: its lanes reduce among themselves
       const unsigned full = 0xffffffffu;
-      if (a.tpe <= 32) {
-        for (int off = a.tpe >> 1; off > 0; off >>= 1) {
-          num += __shfl_xor_sync(full, num, off);
-          den += __shfl_xor_sync(full, den, off);
-        }
-        if (active && row_first) a.reward[env] = num / den;
-      } else {
-        // Shuffles are the cost of this reduction (one warp-wide SHFL per clock
-        // and SM), so the two sums share one butterfly: in the first round even
-        // lanes keep the numerator and odd lanes the denominator of the pair,
-        // the other four rounds then move ONE value per lane.  Lane 0 ends up
-        // with the warp's numerator, lane 1 with its denominator.
-        {
-          const bool odd = (t & 1) != 0;
-          T acc = (odd ? den : num) + __shfl_xor_sync(full, odd ? num : den, 1);
-          for (int off = 2; off <= 16; off <<= 1) acc += __shfl_xor_sync(full, acc, off);
-          if ((t & 31) == 0) sm.s_num[t >> 5] = acc;
-          if ((t & 31) == 1) sm.s_den[t >> 5] = acc;
-        }
-        consumer_sync(NC);
-        if (active && row_first) {
-          const int w0 = t >> 5, nw = a.tpe >> 5;
-          T n = sm.s_num[w0], d = sm.s_den[w0];
-          for (int j = 1; j < nw; ++j) { n += sm.s_num[w0 + j]; d += sm.s_den[w0 + j]; }
-          a.reward[env] = n / d;
-        }
+      for (int off = a.tpe >> 1; off > 0; off >>= 1) {
+        num += __shfl_xor_sync(full, num, off);
+        den += __shfl_xor_sync(full, den, off);
       }
+      if (active && row_first) a.reward[env] = num / den;
     }
     if (++s == PIPE_STAGES) { s = 0; ph_in ^= 1; }
     if (++o == PIPE_OUT) { o = 0; ph_out ^= 1; }

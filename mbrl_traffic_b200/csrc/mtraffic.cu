@@ -110,6 +110,8 @@ __global__ void set_params_kernel(const ParamArgs<T> p) {
   row[TBL_G_CRIT] = g;
   row[TBL_C] = c;
   row[TBL_INV_C] = A::div(T(1), c);
+  row[TBL_FLAGS] = (T)fl;
+  for (int k = TBL_FLAGS + 1; k < TBL_STRIDE; ++k) row[k] = T(0);
   p.flags[env] = fl;
 }
 
@@ -455,39 +457,46 @@ int pipe_vectors_per_thread() {
 
 
 // ---- non-local model launchers ------------------------------------------------
-template <typename T, bool FAST, int LAMK, bool UNIFORM, int U>
-int launch_nl(const NlArgs<T>& na, int grid, cudaStream_t stream) {
+template <typename T, bool FAST, int LAMK, bool UNIFORM, int U, bool LXF>
+int launch_nl_scheme(const NlArgs<T>& na, int grid, cudaStream_t stream) {
   static bool configured_dev[MAX_DEVICES] = {};
   bool* cfg_flag = configured_flag(configured_dev);
   bool unused_flag = false;
   bool& configured = cfg_flag ? *cfg_flag : unused_flag;
   const size_t smem = sizeof(NlSmem<T>);
   if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(nonlocal_pipe_kernel<T, FAST, LAMK, UNIFORM, U>,
+    CUDA_TRY(cudaFuncSetAttribute(nonlocal_pipe_kernel<T, FAST, LAMK, UNIFORM, U, LXF>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  nonlocal_pipe_kernel<T, FAST, LAMK, UNIFORM, U><<<grid, na.nc + 32, smem, stream>>>(na);
+  nonlocal_pipe_kernel<T, FAST, LAMK, UNIFORM, U, LXF><<<grid, na.nc + 32, smem, stream>>>(na);
   return MT_OK;
 }
 
+template <typename T, bool FAST, int LAMK, bool UNIFORM, int U>
+int launch_nl(const NlArgs<T>& na, int grid, cudaStream_t stream, bool lxf = false) {
+  if (lxf) return launch_nl_scheme<T, FAST, LAMK, UNIFORM, U, true>(na, grid, stream);
+  return launch_nl_scheme<T, FAST, LAMK, UNIFORM, U, false>(na, grid, stream);
+}
+
 template <typename T, bool FAST, int U>
-int launch_nl_lam(const NlArgs<T>& na, int grid, bool uniform, int lamk, cudaStream_t s) {
+int launch_nl_lam(const NlArgs<T>& na, int grid, bool uniform, int lamk, cudaStream_t s,
+                  bool lxf) {
   if (uniform && lamk == LAM_ONE && na.u.rho_max == T(1))
-    return launch_nl<T, FAST, LAM_ONE_RM1, true, U>(na, grid, s);
-  if (uniform && lamk == LAM_ONE) return launch_nl<T, FAST, LAM_ONE, true, U>(na, grid, s);
-  if (uniform && lamk == LAM_TWO) return launch_nl<T, FAST, LAM_TWO, true, U>(na, grid, s);
-  if (uniform && lamk == LAM_HALF) return launch_nl<T, FAST, LAM_HALF, true, U>(na, grid, s);
-  return launch_nl<T, FAST, LAM_RUNTIME, false, U>(na, grid, s);
+    return launch_nl<T, FAST, LAM_ONE_RM1, true, U>(na, grid, s, lxf);
+  if (uniform && lamk == LAM_ONE) return launch_nl<T, FAST, LAM_ONE, true, U>(na, grid, s, lxf);
+  if (uniform && lamk == LAM_TWO) return launch_nl<T, FAST, LAM_TWO, true, U>(na, grid, s, lxf);
+  if (uniform && lamk == LAM_HALF) return launch_nl<T, FAST, LAM_HALF, true, U>(na, grid, s, lxf);
+  return launch_nl<T, FAST, LAM_RUNTIME, false, U>(na, grid, s, lxf);
 }
 
 template <typename T, int U>
 int launch_nl_fast(const NlArgs<T>& na, int grid, bool fast, bool uniform, int lamk,
-                   cudaStream_t s) {
+                   cudaStream_t s, bool lxf) {
   if constexpr (FastAllowed<T>::value) {
-    if (fast) return launch_nl_lam<T, true, U>(na, grid, uniform, lamk, s);
+    if (fast) return launch_nl_lam<T, true, U>(na, grid, uniform, lamk, s, lxf);
   }
-  return launch_nl_lam<T, false, U>(na, grid, uniform, lamk, s);
+  return launch_nl_lam<T, false, U>(na, grid, uniform, lamk, s, lxf);
 }
 
 template <typename T>
@@ -499,6 +508,8 @@ int step_nonlocal(mt_engine* e, const T* obs_in, const T* action, T* obs_out, T*
   const int N = (int)e->cfg.n_cells;
   const int n_eta = p.n_eta;
   const bool fast = FastAllowed<T>::value && (p.flags & MT_FLAG_FAST_MATH) != 0;
+  const bool lxf = p.scheme == MT_SCHEME_LXF;
+  const T half_alpha = p.alpha < 0 ? T(-1) : (T)(0.5 * p.alpha);
   if (n_eta > N) return fail(MT_EINVAL, "non-local: n_eta (%d) exceeds n_cells (%d)", n_eta, N);
   int U = pipe_vectors_per_thread();
   if (U == 0) U = (sizeof(T) == 8) ? 2 : 1;
@@ -528,10 +539,11 @@ int step_nonlocal(mt_engine* e, const T* obs_in, const T* action, T* obs_out, T*
     na.B = (int)B; na.N = N;
     na.n_tiles = (int)((B + na.epc - 1) / na.epc);
     na.bc = bc; na.step = step; na.u = uniform_of<T>(e);
+    na.half_alpha = half_alpha;
     const long long slots = 2LL * e->sm_count;
     const int grid = (int)(na.n_tiles < slots ? na.n_tiles : slots);
-    const int rc = U == 2 ? launch_nl_fast<T, 2>(na, grid, fast, e->uniform, e->lamk, stream)
-                          : launch_nl_fast<T, 1>(na, grid, fast, e->uniform, e->lamk, stream);
+    const int rc = U == 2 ? launch_nl_fast<T, 2>(na, grid, fast, e->uniform, e->lamk, stream, lxf)
+                          : launch_nl_fast<T, 1>(na, grid, fast, e->uniform, e->lamk, stream, lxf);
     if (rc != MT_OK) return rc;
     e->launches++;
   } else {
@@ -542,8 +554,14 @@ int step_nonlocal(mt_engine* e, const T* obs_in, const T* action, T* obs_out, T*
     const int block = 256;
     const long long grid = (cells + block - 1) / block;
     if (grid > 0x7fffffffLL) return fail(MT_EINVAL, "batch too large for one launch");
-    if (fast) nonlocal_scalar_kernel<T, FastAllowed<T>::value><<<(unsigned)grid, block, 0, stream>>>(sa);
-    else nonlocal_scalar_kernel<T, false><<<(unsigned)grid, block, 0, stream>>>(sa);
+    sa.half_alpha = half_alpha;
+    if (lxf) {
+      if (fast) nonlocal_lxf_scalar_kernel<T, FastAllowed<T>::value><<<(unsigned)grid, block, 0, stream>>>(sa);
+      else nonlocal_lxf_scalar_kernel<T, false><<<(unsigned)grid, block, 0, stream>>>(sa);
+    } else {
+      if (fast) nonlocal_scalar_kernel<T, FastAllowed<T>::value><<<(unsigned)grid, block, 0, stream>>>(sa);
+      else nonlocal_scalar_kernel<T, false><<<(unsigned)grid, block, 0, stream>>>(sa);
+    }
     e->launches++;
     if (reward_out) {
       const int wpb = 8;
@@ -805,6 +823,19 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
     pa.tpe = pa.nthr <= 32 ? next_pow2(pa.nthr) : ((pa.nthr + 31) / 32) * 32;
     pa.epc = pa.nc / pa.tpe;
     if (pa.epc > PIPE_MAX_EPC) pa.epc = PIPE_MAX_EPC;
+    // per-road parameter table: the tile's table rows ride in the input stage
+    // behind its roads when they fit (a 16 KB stage holds 16000 B of a
+    // 1000-cell f64 road); otherwise the consumers read them from global memory
+    int tbl_off = 0;
+    if (!e->uniform && n_inner == 1) {
+      const long long row_bytes = 2LL * N * (long long)sizeof(T);
+      const int tbl_row = TBL_STRIDE * (int)sizeof(T);
+      const int fit = (int)(PIPE_TILE_BYTES / (row_bytes + tbl_row));
+      if (fit >= 1) {
+        if (pa.epc > fit) pa.epc = fit;
+        tbl_off = PIPE_TILE_BYTES - pa.epc * tbl_row;
+      }
+    }
     const long long n_tiles = (B + pa.epc - 1) / pa.epc;
     if (n_tiles > 0x7fffffffLL) return fail(MT_EINVAL, "batch too large for one launch");
     pa.n_tiles = (int)n_tiles;
@@ -841,6 +872,7 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
                              (!(p.flags & MT_FLAG_DEPENDENT_INPUT) && auto_independent() && disjoint);
     const bool is_ring = pipe_use_ring(sizeof(T) == 4, fast, e->cfg.model == MT_MODEL_ARZ,
                                        pa.sched != nullptr);
+    pa.tbl_off = is_ring ? 0 : tbl_off;
     pa.early_loads = (independent && e->uniform && action == nullptr && reward_out == nullptr &&
                       n_inner == 1 && pipe_use_pdl() && full_grid && !is_ring &&
                       prev.full_pipe) ? 1 : 0;
@@ -1096,6 +1128,10 @@ int mt_set_params(mt_engine* e, const mt_params* p, void* stream) {
   if (!valid_bc(p->bc_left) || !valid_bc(p->bc_right))
     return fail(MT_EINVAL, "Unknown boundary conditions: (%d, %d)", p->bc_left, p->bc_right);
   if (!(p->dx > 0) || !(p->dt > 0)) return fail(MT_EINVAL, "mt_set_params: dx and dt must be > 0");
+  if (p->scheme != MT_SCHEME_GODUNOV && p->scheme != MT_SCHEME_LXF)
+    return fail(MT_EINVAL, "mt_set_params: unknown scheme %d", p->scheme);
+  if (p->scheme == MT_SCHEME_LXF && e->cfg.model != MT_MODEL_NONLOCAL)
+    return fail(MT_EINVAL, "mt_set_params: MT_SCHEME_LXF belongs to the non-local model");
   if (e->cfg.model == MT_MODEL_NONLOCAL) {
     if (p->n_eta < 1 || p->n_eta > e->cfg.max_n_eta || !p->gamma)
       return fail(MT_EINVAL, "mt_set_params: n_eta=%d outside [1, %d] or gamma NULL",

@@ -127,7 +127,7 @@ class Engine(object):
     def set_params(self, dx, dt, rho_max, v_max, lam, boundary_conditions,
                    tau=1.0, rho_crit=None, gamma=None, fast_math=False,
                    no_pipeline=False, independent_input=False, dependent_input=False,
-                   stream=None):
+                   scheme="godunov", alpha=None, stream=None):
         """``mt_set_params``.  rho_max / v_max / tau / lam / rho_crit may be
         Python scalars or device tensors of shape (n_envs,) in the engine
         dtype; ``gamma`` is a device tensor of look-ahead weights."""
@@ -166,6 +166,10 @@ class Engine(object):
             keep["gamma"] = gamma
             p.gamma = gamma.data_ptr()
             p.n_eta = int(gamma.numel())
+        if scheme not in ("godunov", "lxf"):
+            raise ValueError("Unknown scheme: {}".format(scheme))
+        p.scheme = _lib.MT_SCHEME_LXF if scheme == "lxf" else _lib.MT_SCHEME_GODUNOV
+        p.alpha = -1.0 if alpha is None else float(alpha)
         p.flags = (_lib.MT_FLAG_FAST_MATH if fast_math else 0) | \
             (_lib.MT_FLAG_NO_PIPELINE if no_pipeline else 0) | \
             (_lib.MT_FLAG_INDEPENDENT_INPUT if independent_input else 0) | \

@@ -6,7 +6,9 @@ but never implemented it.  This class follows the same ``Model`` contract as
 ``LWRModel`` and the scheme of the paper the reference cites at
 ``lwr.py:209-211`` (Friedrich, Kolb, Goettlich, NHM 13, 2018): drivers adapt
 their speed to a weighted mean of the downstream equilibrium speeds over a
-look-ahead distance ``eta``.
+look-ahead distance ``eta``.  ``scheme="lxf"`` selects the other classical
+variant instead: the speed of a weighted mean of the downstream DENSITIES with
+a Lax-Friedrichs flux (Blandin & Goatin, Numer. Math. 132, 2016).
 """
 import json
 import os
@@ -45,6 +47,8 @@ class NonLocalModel(FiniteVolumeModel):
     conditions: ``"loop"`` is a true periodic ring for this model,
     ``"extend_both"``, ``{"constant_both": (rho_l, rho_r)}`` and
     ``{"inflow_outflow": rho_l}`` (fixed inflow density, free outflow).
+    ``scheme``: ``"godunov"`` (default) or ``"lxf"``; ``alpha`` is the LxF
+    viscosity (None: each road's ``v_max``, the bound of ``|V|``).
 
     ``get_next_obs`` keeps the reference observation layout ``[rho | v]``;
     like ``LWRModel`` the input velocity is ignored and the output velocity is
@@ -73,7 +77,11 @@ class NonLocalModel(FiniteVolumeModel):
                  boundary_conditions,
                  optimizer_cls,
                  optimizer_params=None,
+                 scheme="godunov",
+                 alpha=None,
                  **engine_kwargs):
+        if scheme not in ("godunov", "lxf"):
+            raise ValueError("Unknown scheme: {}".format(scheme))
         super(NonLocalModel, self).__init__(
             sess=sess, ob_space=ob_space, ac_space=ac_space,
             replay_buffer=replay_buffer, verbose=verbose, **engine_kwargs)
@@ -87,6 +95,8 @@ class NonLocalModel(FiniteVolumeModel):
         self.lam = lam
         self.eta = eta
         self.kernel = kernel
+        self.scheme = scheme
+        self.alpha = alpha
         self.boundary_conditions = boundary_conditions
         self.optimizer_cls = optimizer_cls
         self.optimizer_params = optimizer_params or {}
@@ -113,13 +123,20 @@ class NonLocalModel(FiniteVolumeModel):
         return 256
 
     def _engine_kwargs(self):
-        return {"gamma": self.weights()}
+        return {"gamma": self.weights(), "scheme": self.scheme, "alpha": self.alpha}
 
     def cfl_number(self):
-        """dt/dx * (gamma_0 |V'|_max rho_max + |V|_max); the scheme is
-        monotone for values <= 1 (Friedrich et al. 2018, Thm 3.1; lam = 1)."""
+        """Godunov scheme: dt/dx * (gamma_0 |V'|_max rho_max + |V|_max); the
+        scheme is monotone for values <= 1 (Friedrich et al. 2018, Thm 3.1;
+        lam = 1).  LxF scheme: dt/dx * (alpha + gamma_0 |V'|_max rho_max) with
+        the same bound (Blandin & Goatin 2016, condition (3.5) up to their
+        factor conventions)."""
         g0 = float(self.weights()[0])
-        return self.dt / self.dx * (g0 * np.max(self.v_max) + np.max(self.v_max))
+        v = float(np.max(self.v_max))
+        if self.scheme == "lxf":
+            alpha = v if self.alpha is None else float(self.alpha)
+            return self.dt / self.dx * (alpha + g0 * v)
+        return self.dt / self.dx * (g0 * v + v)
 
     def update(self):
         if self.optimizer is None:
@@ -130,11 +147,12 @@ class NonLocalModel(FiniteVolumeModel):
 
     _KEYS = ("dx", "dt", "rho_max", "rho_max_max", "v_max", "v_max_max",
              "stream_model", "lam", "eta", "kernel", "boundary_conditions")
+    _OPTIONAL_KEYS = ("scheme", "alpha")
 
     def save(self, save_path):
         """``model.json`` with the LWR keys plus ``eta`` and ``kernel``."""
         with open(os.path.join(save_path, "model.json"), 'w') as f:
-            json.dump({k: getattr(self, k) for k in self._KEYS}, f,
+            json.dump({k: getattr(self, k) for k in self._KEYS + self._OPTIONAL_KEYS}, f,
                       sort_keys=True, indent=4)
 
     def load(self, load_path):
@@ -142,3 +160,6 @@ class NonLocalModel(FiniteVolumeModel):
             data = json.load(f)
         for key in self._KEYS:
             setattr(self, key, data[key])
+        for key in self._OPTIONAL_KEYS:
+            if key in data:
+                setattr(self, key, data[key])

@@ -331,6 +331,45 @@ def nonlocal_step(obs, gamma, dx=50, dt=0.5, rho_max=1, v_max=30, lam=1,
     return out[0] if squeeze else out
 
 
+def nonlocal_lxf_step(obs, gamma, dx=50, dt=0.5, rho_max=1, v_max=30, lam=1,
+                      boundary_conditions="loop", alpha=None):
+    """Lax-Friedrichs-type step of the non-local LWR model whose speed depends
+    on a downstream average of the DENSITY (Blandin & Goatin, Numer. Math. 132
+    (2016), scheme (3.2)-(3.4); the second scheme BASELINE.json's north_star
+    names).  PARITY UNPINNED: the reference holds no code for it.
+
+        R_j       = sum_{k=0}^{n_eta-1} gamma_k rho_{j+k}        (k ascending)
+        g_j       = rho_j V(R_j)
+        F_{j+1/2} = 0.5 (g_j + g_{j+1}) + (0.5 alpha) (rho_j - rho_{j+1})
+        rho'_j    = rho_j - (dt/dx) (F_{j+1/2} - F_{j-1/2})
+
+    ``alpha`` is the numerical viscosity, >= max |V| (default: v_max; the
+    scheme is monotone for dt/dx <= 1 / (alpha + gamma_0 |V'| rho_max)-ish
+    step sizes, see the paper's CFL condition (3.5)).  Ghost cells as in
+    ``nonlocal_step`` (one upstream, n_eta downstream).  The weights are the
+    cell integrals ``nonlocal_weights`` returns (the paper uses left-endpoint
+    values w(k dx) dx; both are consistent quadratures of the same kernel).
+    """
+    rho, _, squeeze = _split(obs)
+    gamma = np.asarray(gamma, dtype=rho.dtype)
+    n_eta = gamma.shape[0]
+    n = rho.shape[1]
+    step = dt / dx
+    ext = _nonlocal_ghosts(rho, n_eta, boundary_conditions)   # cells -1 .. N+n_eta-1
+    # R for cells -1 .. N  (ext index c+1 <-> cell c)
+    r = np.zeros((rho.shape[0], n + 2), dtype=rho.dtype)
+    for k in range(n_eta):
+        r = r + gamma[k] * ext[:, k:k + n + 2]
+    cells = ext[:, :n + 2]
+    g = cells * v_eq(r, v_max, rho_max, lam)
+    half_alpha = 0.5 * _col(v_max if alpha is None else alpha, rho.dtype)
+    flux = 0.5 * (g[:, :-1] + g[:, 1:]) + half_alpha * (cells[:, :-1] - cells[:, 1:])
+    rho_tp1 = rho - step * (flux[:, 1:] - flux[:, :-1])       # faces -1/2 .. N-1/2
+    v_tp1 = v_eq(rho_tp1, v_max, rho_max, lam)
+    out = np.concatenate((rho_tp1, v_tp1), axis=1)
+    return out[0] if squeeze else out
+
+
 # --------------------------------------------------------------------------- #
 # drivers                                                                     #
 # --------------------------------------------------------------------------- #

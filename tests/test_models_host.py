@@ -132,7 +132,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_header_layout():
     import ctypes
     assert ctypes.sizeof(_lib.MtConfig) == 40
-    assert ctypes.sizeof(_lib.MtParams) == 7 * 8 + 5 * 8 + 8 + 32 + 8 + 8
+    assert ctypes.sizeof(_lib.MtParams) == 7 * 8 + 5 * 8 + 8 + 32 + 8 + 8 + 8 + 8
 
 
 def test_no_cpu_fallback_without_gpu():

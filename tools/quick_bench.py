@@ -40,6 +40,8 @@ def main():
     ap.add_argument("--independent", action="store_true",
                     help="MT_FLAG_INDEPENDENT_INPUT (valid for the streaming measurement only)")
     ap.add_argument("--lam", type=float, default=1.0)
+    ap.add_argument("--scheme", default="godunov", help="non-local model: godunov | lxf")
+    ap.add_argument("--action", action="store_true", help="pass a per-road speed limit")
     ap.add_argument("--bc", default="loop",
                     help="loop | extend_both | inflow_outflow (constant 0.3 rho_max inflow, "
                          "free outflow: BASELINE config 3)")
@@ -67,12 +69,12 @@ def main():
         eng.set_params(dx=50, dt=0.5, rho_max=rnd(0.9, 1.5) * args.rho_max, v_max=rnd(20, 40),
                        lam=rnd(0.5, 3.0), boundary_conditions=bc, tau=rnd(5, 25),
                        fast_math=args.fast, no_pipeline=args.direct, gamma=gamma,
-                       independent_input=args.independent)
+                       independent_input=args.independent, scheme=args.scheme)
     else:
         eng.set_params(dx=50, dt=0.5, rho_max=par(args.rho_max), v_max=par(30),
                        lam=par(args.lam), boundary_conditions=bc, tau=par(9),
                        fast_math=args.fast, no_pipeline=args.direct, gamma=gamma,
-                       independent_input=args.independent)
+                       independent_input=args.independent, scheme=args.scheme)
     rng = np.random.default_rng(0)
     rho = args.rho_max * rng.uniform(0.05, 0.9, (b, n))
     v = 30 * (1 - rho / args.rho_max) + rng.normal(0, 1, (b, n))
@@ -80,6 +82,7 @@ def main():
     ins = [obs.clone() for _ in range(args.sets)]
     outs = [torch.empty_like(obs) for _ in range(args.sets)]
     rew = torch.empty(b, dtype=tdt, device="cuda") if args.reward else None
+    act = torch.full((b,), 25.0, dtype=tdt, device="cuda") if args.action else None
     esz = obs.element_size()
     cells = b * n
 
@@ -87,12 +90,12 @@ def main():
         if chained:
             a, c = ins[0], outs[0]
             for _ in range(k):
-                eng.step(a, c, reward=rew)
+                eng.step(a, c, reward=rew, action=act)
                 a, c = c, a
         else:
             for i in range(k):
                 j = i % args.sets
-                eng.step(ins[j], outs[j], reward=rew)
+                eng.step(ins[j], outs[j], reward=rew, action=act)
 
     res = {}
     side = torch.cuda.Stream()
