@@ -305,6 +305,8 @@ template <typename T, int MODEL, bool FAST> struct PipeDynamic {
 // MODEL: 0 = LWR, 1 = ARZ.  LAMK: exponent kind fixed at compile time, or
 // LAM_RUNTIME.  UNIFORM: every road shares the scalar parameters in a.u.
 // U: 16-byte vectors (of each field) per thread; a thread owns U*V cells.
+// (288 threads are allocated as 10 warps: 96 registers per thread is what two
+// CTAs per SM leave; a build with __maxnreg__(112) ran one CTA per SM, 35 us)
 template <typename T, int MODEL, bool FAST, int LAMK, bool UNIFORM, int U>
 __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kernel(const PipeArgs<T> a) {
   constexpr int V = Vec<T>::N;

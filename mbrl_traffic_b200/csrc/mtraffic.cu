@@ -304,13 +304,28 @@ bool auto_independent() {
 // the producer-warp kernel has (B200, 16384x1000 f32 EXACT: ARZ 82 % ring vs
 // 74 % pipe, LWR 79 % ring vs 91 % pipe of HBM peak).
 // MT_KERNEL=pipe|ring overrides for A/B runs.
-bool pipe_use_ring(bool is_f32, bool fast, bool arz, bool dynamic) {
+// A per-road parameter table costs ARZ f64 about 16 more live registers: the
+// producer-warp kernel is held to 96 per thread (288 threads are allocated as
+// 10 warps) and spills, the ring kernel (256 threads, 128 registers) does not
+// (4096 x 1000, lam = 1: 37 us vs 48 us per step).
+bool pipe_use_ring(bool is_f32, bool fast, bool arz, bool dynamic, bool uniform) {
   static int v = -1;
   if (v < 0) {
     const char* s = getenv("MT_KERNEL");
     v = !s ? 2 : (s[0] == 'r') ? 1 : 0;
   }
-  if (v == 2) return is_f32 && !fast && (arz || !dynamic);
+  if (v == 2) return (is_f32 && !fast && (arz || !dynamic)) || (!is_f32 && arz && !uniform);
+  return v != 0;
+}
+
+// MT_TABLE_STAGE=0: the pipelined kernel's consumers read their table rows from
+// global memory instead of a copy staged with the tile (A/B knob)
+bool pipe_stage_table() {
+  static int v = -1;
+  if (v < 0) {
+    const char* s = getenv("MT_TABLE_STAGE");
+    v = (s && s[0] == '0') ? 0 : 1;
+  }
   return v != 0;
 }
 
@@ -357,7 +372,7 @@ int launch_pipe(const PipeArgs<T>& pa, int grid, cudaStream_t stream) {
                                   (int)sizeof(RingSmem<T, U>)));
     configured = true;
   }
-  if (pa.n_inner == 1 && pipe_use_ring(sizeof(T) == 4, FAST, MODEL == 1, pa.sched != nullptr))
+  if (pa.n_inner == 1 && pipe_use_ring(sizeof(T) == 4, FAST, MODEL == 1, pa.sched != nullptr, UNIFORM))
     return launch_pdl(step_ring_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>, pa, grid, pa.nc,
                       sizeof(RingSmem<T, U>), stream);
   if (pa.n_inner > 1)
@@ -827,7 +842,7 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
     // behind its roads when they fit (a 16 KB stage holds 16000 B of a
     // 1000-cell f64 road); otherwise the consumers read them from global memory
     int tbl_off = 0;
-    if (!e->uniform && n_inner == 1) {
+    if (!e->uniform && n_inner == 1 && pipe_stage_table()) {
       const long long row_bytes = 2LL * N * (long long)sizeof(T);
       const int tbl_row = TBL_STRIDE * (int)sizeof(T);
       const int fit = (int)(PIPE_TILE_BYTES / (row_bytes + tbl_row));
@@ -863,7 +878,8 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
     // here on the byte ranges, or vouched for by the caller
     // (MT_FLAG_INDEPENDENT_INPUT).  MT_FLAG_DEPENDENT_INPUT turns the check
     // off: every launch waits.  Consumers must not touch global memory before
-    // the wait: scalar parameters, no speed limits, no rewards.
+    // the wait: scalar parameters, no speed limits; rewards only when the
+    // producer thread stores them (roads wider than a warp), after its wait.
     const bool full_grid = (long long)grid == slots;
     const char* in_lo = (const char*)obs_in;
     const char* in_hi = in_lo + (size_t)B * 2 * N * sizeof(T);
@@ -871,10 +887,10 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
     const bool independent = (p.flags & MT_FLAG_INDEPENDENT_INPUT) ||
                              (!(p.flags & MT_FLAG_DEPENDENT_INPUT) && auto_independent() && disjoint);
     const bool is_ring = pipe_use_ring(sizeof(T) == 4, fast, e->cfg.model == MT_MODEL_ARZ,
-                                       pa.sched != nullptr);
+                                       pa.sched != nullptr, e->uniform);
     pa.tbl_off = is_ring ? 0 : tbl_off;
-    pa.early_loads = (independent && e->uniform && action == nullptr && reward_out == nullptr &&
-                      n_inner == 1 && pipe_use_pdl() && full_grid && !is_ring &&
+    pa.early_loads = (independent && e->uniform && action == nullptr &&
+                      (reward_out == nullptr || pa.tpe > 32) && n_inner == 1 && pipe_use_pdl() && full_grid && !is_ring &&
                       prev.full_pipe) ? 1 : 0;
     StreamNote mine;
     mine.device = e->cfg.device;
