@@ -179,6 +179,27 @@ int mt_set_params(mt_engine *e, const mt_params *p, void *stream);
 int mt_step(mt_engine *e, const void *obs_in, const void *action,
             void *obs_out, void *reward_out, void *stream);
 
+/* mt_step that also leaves a bfloat16 copy of the new state in obs_out_bf16
+ * (DEVICE, (B, 2N) row-major, 8-byte aligned): what a policy network reads
+ * next, written by the step kernel while the values are still in registers
+ * instead of a separate conversion pass over obs_out.  (The rollout loop the
+ * reference intends, policies/kshoot.py:65-85 / algorithm.py:564-620: policy
+ * -> model step -> reward, every step.) */
+int mt_step_obs16(mt_engine *e, const void *obs_in, const void *action,
+                  void *obs_out, void *reward_out, void *obs_out_bf16,
+                  void *stream);
+
+/* Output layer of a feed-forward speed-limit policy fused with its squashing
+ * (the actor shape of policies/sac.py:303-322 with the action range of
+ * envs/vsl.py:92-100):  action[b] = scale * (tanh(hidden[b,:] . weight + bias)
+ * + 1), hidden (B, n_hidden) / weight (n_hidden) / bias (1) bfloat16 DEVICE
+ * arrays, action in `dtype` (mt_dtype) -- the buffer mt_step reads its speed
+ * limits from.  Asynchronous on stream. */
+int mt_actor_head(int32_t device, int32_t dtype, const void *hidden_bf16,
+                  const void *weight_bf16, const void *bias_bf16,
+                  void *action_out, int64_t n_envs, int32_t n_hidden,
+                  double scale, void *stream);
+
 /* n_steps chained steps ping-ponging between two caller-owned DEVICE batches,
  * starting from obs_a.  actions: DEVICE [n_steps, B] or NULL.  rewards:
  * DEVICE [n_steps, B] or NULL.  *result_in_b is set to 1 when the final state

@@ -193,6 +193,43 @@ class FiniteVolumeModel(Model):
             out = res
         return out[0] if squeeze else out
 
+    def trajectory(self, obs, actions=None, n_steps=1):
+        """The states of ``n_steps`` chained steps, ``(n_steps + 1, batch, 2N)``
+        (``(n_steps + 1, 2N)`` for one road), first entry = ``obs``: the loop of
+        experiments/evaluate_model.py:388-414, which keeps every frame for its
+        CSV / heat map.  The frames are written where they stay -- step k reads
+        slice k of the trajectory buffer on the device and writes slice k + 1
+        -- so a NumPy caller pays ONE upload and ONE download instead of a
+        PCIe round trip per step.  ``actions``: ``(n_steps, batch)`` speed
+        limits (used only with ``action_is_speed_limit``)."""
+        import torch
+        dev = "cuda:%d" % self.device
+        was_torch = _is_torch(obs)
+        if was_torch:
+            first = obs
+        else:
+            arr = np.asarray(obs)
+            if arr.dtype not in (np.float32, np.float64):
+                arr = arr.astype(np.float64)
+            first = torch.as_tensor(np.ascontiguousarray(arr), device=dev)
+        squeeze = first.dim() == 1
+        first = (first.unsqueeze(0) if squeeze else first).contiguous()
+        if first.dim() != 2 or first.shape[1] % 2:
+            raise ValueError("obs must be (2N,) or (batch, 2N)")
+        n_envs, n_cells = first.shape[0], first.shape[1] // 2
+        eng = self._get_engine(n_envs, n_cells, dtype_name(first.dtype), host=False)
+        traj = torch.empty((n_steps + 1,) + tuple(first.shape), dtype=first.dtype,
+                           device=first.device)
+        traj[0].copy_(first)
+        acts = None
+        if actions is not None and self.action_is_speed_limit:
+            acts = torch.as_tensor(actions, device=first.device).to(first.dtype) \
+                .reshape(n_steps, n_envs).contiguous()
+        for k in range(n_steps):
+            eng.step(traj[k], traj[k + 1], action=None if acts is None else acts[k])
+        out = traj[:, 0] if squeeze else traj
+        return out if was_torch else out.cpu().numpy()
+
     # ------------------------------------------------------------------ #
     # loss                                                               #
     # ------------------------------------------------------------------ #

@@ -28,7 +28,7 @@ EXPORTS = (
     "mt_launch_count", "mt_alloc_pinned", "mt_free_pinned", "mt_aggregate",
     "mt_nonfinite", "mt_halo_create", "mt_halo_destroy", "mt_halo_handle", "mt_halo_connect",
     "mt_halo_connect_local", "mt_halo_push", "mt_halo_pull", "mt_halo_status",
-    "mt_halo_advance",
+    "mt_halo_advance", "mt_step_obs16", "mt_actor_head",
 )
 
 
@@ -95,6 +95,10 @@ def load():
     lib.mt_set_params.argtypes = [vp, ctypes.POINTER(MtParams), vp]
     lib.mt_step.restype = ctypes.c_int
     lib.mt_step.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.mt_step_obs16.restype = ctypes.c_int
+    lib.mt_step_obs16.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.mt_actor_head.restype = ctypes.c_int
+    lib.mt_actor_head.argtypes = [i32, i32, vp, vp, vp, vp, i64, i32, ctypes.c_double, vp]
     lib.mt_rollout.restype = ctypes.c_int
     lib.mt_rollout.argtypes = [vp, vp, vp, vp, vp, i32, vp,
                                ctypes.POINTER(i32)]

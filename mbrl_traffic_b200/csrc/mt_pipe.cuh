@@ -31,11 +31,24 @@
 // MT_FLAG_INDEPENDENT_INPUT it issues the first ring-full of loads outright.
 #pragma once
 #include <stdint.h>
+#include <cuda_bf16.h>
 #include "mtraffic.h"
 #include "mt_math.cuh"
 #include "mt_cell.cuh"
 
 namespace mt {
+
+// four values -> four bfloat16 (round to nearest even, through f32 like a
+// torch .to(bfloat16)) packed in 8 bytes
+template <typename T>
+__device__ __forceinline__ uint2 pack_bf16x4(T a, T b, T c, T d) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn((float)a, (float)b);
+  const __nv_bfloat162 hi = __floats2bfloat162_rn((float)c, (float)d);
+  uint2 out;
+  out.x = *reinterpret_cast<const uint32_t*>(&lo);
+  out.y = *reinterpret_cast<const uint32_t*>(&hi);
+  return out;
+}
 
 #ifndef MT_PIPE_CTAS
 #define MT_PIPE_CTAS 2                            // resident CTAs per SM the kernel is sized for
@@ -287,6 +300,9 @@ template <typename T> struct PipeArgs {
   // (they fit behind the roads: the host picks epc accordingly); 0: the
   // consumers read their rows from global memory instead.
   int tbl_off = 0;
+  // mt_step_obs16: a bfloat16 copy of the new state, (B, 2N) row-major, for a
+  // policy network that reads the observation next (nullptr: none)
+  uint16_t* obs16 = nullptr;
 };
 
 // Which instantiations of step_pipe_kernel draw their tiles from a counter.
@@ -708,6 +724,22 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
         for (int k = 0; k < V; ++k) { tr[k] = rn[u * V + k]; tv[k] = vn[u * V + k]; }
         sts16(dst + 16 * u, tr);
         sts16(dst + v_off + 16 * u, tv);
+      }
+      if (a.obs16 != nullptr) {
+        // (8-byte stores per four cells of a field, coalesced over the warp)
+        uint16_t* o16 = a.obs16 + (size_t)env * (2 * (size_t)N) + (size_t)pos * CPT;
+        if constexpr (CPT % 4 == 0) {
+#pragma unroll
+          for (int q = 0; q < CPT / 4; ++q) {
+            *reinterpret_cast<uint2*>(o16 + 4 * q) =
+                pack_bf16x4(rn[4 * q], rn[4 * q + 1], rn[4 * q + 2], rn[4 * q + 3]);
+            *reinterpret_cast<uint2*>(o16 + N + 4 * q) =
+                pack_bf16x4(vn[4 * q], vn[4 * q + 1], vn[4 * q + 2], vn[4 * q + 3]);
+          }
+        } else {   // two cells per thread (f64, one vector)
+          *reinterpret_cast<uint32_t*>(o16) = pack_bf16x4(rn[0], rn[1], rn[0], rn[1]).x;
+          *reinterpret_cast<uint32_t*>(o16 + N) = pack_bf16x4(vn[0], vn[1], vn[0], vn[1]).x;
+        }
       }
     }
     if (want_reward && a.tpe > 32) {

@@ -153,6 +153,45 @@ __global__ void nonfinite_kernel(const T* __restrict__ obs, int* __restrict__ ou
   if (lane == 0) out[env] = bad ? 1 : 0;
 }
 
+// bfloat16 copy of a batch (paths of mt_step_obs16 that do not go through the
+// pipelined kernel, which writes the copy itself): 4 values per thread
+template <typename T>
+__global__ void obs_to_bf16_kernel(const T* __restrict__ obs, uint16_t* __restrict__ out,
+                                   long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    *reinterpret_cast<uint2*>(out + i) = pack_bf16x4(obs[i], obs[i + 1], obs[i + 2], obs[i + 3]);
+  } else {
+    for (long long k = i; k < n; ++k) {
+      const __nv_bfloat16 h = __float2bfloat16_rn((float)obs[k]);
+      out[k] = *reinterpret_cast<const uint16_t*>(&h);
+    }
+  }
+}
+
+// Last layer of the policy MLP fused with its squashing: one warp per road,
+//   action = scale * (tanh(h . w + b) + 1),  h: (B, H) bfloat16,
+// written in the engine dtype straight into the buffer the next mt_step reads
+// its speed limits from (FeedForwardActor, policies/sac.py:303-322 shape).
+template <typename T>
+__global__ void actor_head_kernel(const __nv_bfloat16* __restrict__ h,
+                                  const __nv_bfloat16* __restrict__ w,
+                                  const __nv_bfloat16* __restrict__ bias, T* __restrict__ action,
+                                  long long B, int H, float scale) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const int lane = threadIdx.x & 31;
+  const __nv_bfloat16* hr = h + row * H;
+  float acc = 0.f;
+  for (int k = lane; k < H; k += 32) acc = fmaf(__bfloat162float(hr[k]), __bfloat162float(w[k]), acc);
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) {
+    // the reference layer rounds its output to the activation dtype before tanh
+    const float z = __bfloat162float(__float2bfloat16_rn(acc + __bfloat162float(bias[0])));
+    action[row] = (T)(scale * (tanhf(z) + 1.0f));
+  }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------
@@ -178,6 +217,10 @@ struct mt_engine {
   UniformC<double> u64;
   UniformC<float> u32;
   int64_t launches = 0;
+  // mt_step_obs16: where the step being issued leaves a bfloat16 copy of the
+  // new state (null for every other call); consumed by step_typed
+  uint16_t* obs16 = nullptr;
+  bool obs16_written = false;   // the step kernel wrote it (else step_range converts)
   // table readiness: recorded by mt_set_params, awaited once by the next
   // step issued on a different stream
   cudaEvent_t params_ready = nullptr;
@@ -770,6 +813,7 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
                int n_inner = 1, long long action_stride = -1, long long reward_stride = 0) {
   // (see the early-load bookkeeping in the pipelined branch)
   const StreamNote prev = note_take(e->cfg.device, stream);
+  uint16_t* const obs16 = e->obs16;
   constexpr int V = Vec<T>::N;
   const mt_params& p = e->params;
   const long long B = n_env;
@@ -889,7 +933,11 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
     const bool is_ring = pipe_use_ring(sizeof(T) == 4, fast, e->cfg.model == MT_MODEL_ARZ,
                                        pa.sched != nullptr, e->uniform);
     pa.tbl_off = is_ring ? 0 : tbl_off;
-    pa.early_loads = (independent && e->uniform && action == nullptr &&
+    if (obs16 != nullptr && !is_ring && n_inner == 1) {
+      pa.obs16 = obs16 + env0 * 2 * N;
+      e->obs16_written = true;
+    }
+    pa.early_loads = (independent && e->uniform && action == nullptr && pa.obs16 == nullptr &&
                       (reward_out == nullptr || pa.tpe > 32) && n_inner == 1 && pipe_use_pdl() && full_grid && !is_ring &&
                       prev.full_pipe) ? 1 : 0;
     StreamNote mine;
@@ -1029,11 +1077,29 @@ bool can_fuse_steps(const mt_engine* e, const void* obs_in, const void* obs_out)
 int step_range(mt_engine* e, const void* obs_in, const void* action, void* obs_out,
                void* reward_out, long long env0, long long n_env, cudaStream_t stream,
                int n_inner = 1, long long action_stride = -1, long long reward_stride = 0) {
+  e->obs16_written = false;
+  const int rc = e->cfg.dtype == MT_F64
+      ? step_typed<double>(e, obs_in, action, obs_out, reward_out, env0, n_env, stream, n_inner,
+                           action_stride, reward_stride)
+      : step_typed<float>(e, obs_in, action, obs_out, reward_out, env0, n_env, stream, n_inner,
+                          action_stride, reward_stride);
+  uint16_t* const obs16 = e->obs16;
+  e->obs16 = nullptr;
+  if (rc != MT_OK || obs16 == nullptr || e->obs16_written) return rc;
+  // this batch did not take the kernel that writes the copy itself
+  const long long row = 2LL * e->cfg.n_cells, n = n_env * row;
+  const int block = 256;
+  const long long grid = (n / 4 + block) / block;
+  if (grid > 0x7fffffffLL) return fail(MT_EINVAL, "batch too large for one launch");
   if (e->cfg.dtype == MT_F64)
-    return step_typed<double>(e, obs_in, action, obs_out, reward_out, env0, n_env, stream, n_inner,
-                              action_stride, reward_stride);
-  return step_typed<float>(e, obs_in, action, obs_out, reward_out, env0, n_env, stream, n_inner,
-                           action_stride, reward_stride);
+    obs_to_bf16_kernel<double><<<(unsigned)grid, block, 0, stream>>>(
+        (const double*)obs_out + env0 * row, obs16 + env0 * row, n);
+  else
+    obs_to_bf16_kernel<float><<<(unsigned)grid, block, 0, stream>>>(
+        (const float*)obs_out + env0 * row, obs16 + env0 * row, n);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return MT_OK;
 }
 
 int step_any(mt_engine* e, const void* obs_in, const void* action, void* obs_out,
@@ -1201,6 +1267,45 @@ int mt_step(mt_engine* e, const void* obs_in, const void* action, void* obs_out,
   if (obs_in == obs_out) return fail(MT_EINVAL, "mt_step: obs_in and obs_out must differ");
   CUDA_TRY(cudaSetDevice(e->cfg.device));
   return step_any(e, obs_in, action, obs_out, reward_out, (cudaStream_t)stream);
+}
+
+int mt_step_obs16(mt_engine* e, const void* obs_in, const void* action, void* obs_out,
+                  void* reward_out, void* obs_out_bf16, void* stream) {
+  if (!e || !obs_in || !obs_out) return fail(MT_EINVAL, "mt_step_obs16: NULL argument");
+  if (!e->have_params) return fail(MT_ESTATE, "mt_step_obs16: call mt_set_params first");
+  if (obs_in == obs_out) return fail(MT_EINVAL, "mt_step_obs16: obs_in and obs_out must differ");
+  if (((uintptr_t)obs_out_bf16 & 7u) != 0)
+    return fail(MT_EINVAL, "mt_step_obs16: the bfloat16 batch must be 8-byte aligned");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  e->obs16 = (uint16_t*)obs_out_bf16;
+  const int rc = step_any(e, obs_in, action, obs_out, reward_out, (cudaStream_t)stream);
+  e->obs16 = nullptr;
+  return rc;
+}
+
+int mt_actor_head(int32_t device, int32_t dtype, const void* hidden_bf16, const void* weight_bf16,
+                  const void* bias_bf16, void* action_out, int64_t n_envs, int32_t n_hidden,
+                  double scale, void* stream) {
+  if (!hidden_bf16 || !weight_bf16 || !bias_bf16 || !action_out)
+    return fail(MT_EINVAL, "mt_actor_head: NULL argument");
+  if (n_envs < 0 || n_hidden < 1) return fail(MT_EINVAL, "mt_actor_head: bad sizes");
+  if (dtype != MT_F32 && dtype != MT_F64) return fail(MT_EINVAL, "mt_actor_head: unknown dtype");
+  CUDA_TRY(cudaSetDevice(device));
+  if (n_envs == 0) return MT_OK;
+  const int wpb = 8;
+  const long long grid = (n_envs + wpb - 1) / wpb;
+  if (grid > 0x7fffffffLL) return fail(MT_EINVAL, "batch too large for one launch");
+  note_forget(device, stream);
+  if (dtype == MT_F64)
+    actor_head_kernel<double><<<(unsigned)grid, wpb * 32, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)hidden_bf16, (const __nv_bfloat16*)weight_bf16,
+        (const __nv_bfloat16*)bias_bf16, (double*)action_out, n_envs, n_hidden, (float)scale);
+  else
+    actor_head_kernel<float><<<(unsigned)grid, wpb * 32, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)hidden_bf16, (const __nv_bfloat16*)weight_bf16,
+        (const __nv_bfloat16*)bias_bf16, (float*)action_out, n_envs, n_hidden, (float)scale);
+  CUDA_TRY(cudaGetLastError());
+  return MT_OK;
 }
 
 int mt_rollout(mt_engine* e, void* obs_a, void* obs_b, const void* actions, void* rewards,

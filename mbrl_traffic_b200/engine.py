@@ -178,8 +178,15 @@ class Engine(object):
                                            _stream_ptr(stream)))
         self._keep = keep
 
-    def step(self, obs_in, obs_out, action=None, reward=None, stream=None):
-        """``mt_step`` on device buffers."""
+    def step(self, obs_in, obs_out, action=None, reward=None, stream=None, obs16=None):
+        """``mt_step`` on device buffers; with ``obs16`` (a bfloat16 device
+        tensor shaped like ``obs_out``) ``mt_step_obs16``: the step also leaves
+        a bfloat16 copy of the new state there."""
+        if obs16 is not None:
+            _lib.check(self._lib.mt_step_obs16(
+                self._h, _ptr(obs_in), _ptr(action), _ptr(obs_out), _ptr(reward),
+                _ptr(obs16), _stream_ptr(stream)))
+            return
         _lib.check(self._lib.mt_step(self._h, _ptr(obs_in), _ptr(action),
                                      _ptr(obs_out), _ptr(reward),
                                      _stream_ptr(stream)))
@@ -216,6 +223,23 @@ class Engine(object):
         out = ctypes.c_int64(0)
         _lib.check(self._lib.mt_launch_count(self._h, ctypes.byref(out)))
         return out.value
+
+
+def actor_head(hidden, weight, bias, action_out, scale, stream=None):
+    """``mt_actor_head``: ``action_out[b] = scale * (tanh(hidden[b] . weight +
+    bias) + 1)`` -- the output layer of a speed-limit policy written straight
+    into the engine-dtype buffer ``mt_step`` reads its actions from.  ``hidden``
+    (B, H), ``weight`` (H,) / (1, H), ``bias`` (1,): contiguous bfloat16 device
+    tensors; ``action_out``: (B,) float32 / float64 device tensor."""
+    lib = _lib.load()
+    b, h = hidden.shape
+    if weight.numel() != h or bias.numel() != 1 or action_out.numel() != b:
+        raise ValueError("actor_head: shapes do not match")
+    _lib.check(lib.mt_actor_head(
+        hidden.device.index or 0, _DTYPES[dtype_name(action_out.dtype)], _ptr(hidden),
+        _ptr(weight), _ptr(bias), _ptr(action_out), int(b), int(h), float(scale),
+        _stream_ptr(stream)))
+    return action_out
 
 
 class PinnedArray(object):

@@ -69,12 +69,10 @@ def load_initial_conditions(path, min_density=None):
 def rollout_to_csv(model, obs0, n_steps, path, dt=None):
     """Simulate one road for ``n_steps`` (the loop of
     ``evaluate_model.py:388-403``) and save the trajectory as a macro CSV."""
-    cur = np.asarray(obs0, dtype=np.float64)
-    frames = [cur]
-    for _ in range(n_steps):
-        cur = model.get_next_obs(cur, None)
-        frames.append(cur)
+    # every frame stays on the device until the run is over: one upload, one
+    # download (FiniteVolumeModel.trajectory), not a round trip per step
+    frames = model.trajectory(np.asarray(obs0, dtype=np.float64), n_steps=n_steps)
     dt = model.dt if dt is None else dt
     times = np.arange(len(frames)) * dt
-    write_macro_csv(path, times, np.stack(frames))
-    return times, np.stack(frames)
+    write_macro_csv(path, times, frames)
+    return times, frames

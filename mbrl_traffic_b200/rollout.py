@@ -29,7 +29,9 @@ class BatchedMacroEnv(object):
     """
 
     def __init__(self, model, n_envs, n_cells, horizon=500, dtype=torch.float64,
-                 device=None):
+                 device=None, obs_bf16=False):
+        """``obs_bf16``: every step also leaves a bfloat16 copy of the new
+        state in ``self.obs16`` (``mt_step_obs16``) for a policy network."""
         self.model = model
         self.n_envs, self.n_cells, self.horizon = n_envs, n_cells, horizon
         self.dtype = dtype
@@ -40,6 +42,8 @@ class BatchedMacroEnv(object):
                       for _ in range(2)]
         self._cur = 0
         self.reward = torch.empty(n_envs, dtype=dtype, device=self.device)
+        self.obs16 = torch.empty(n_envs, 2 * n_cells, dtype=torch.bfloat16,
+                                 device=self.device) if obs_bf16 else None
         self.t = 0
 
     @property
@@ -50,6 +54,8 @@ class BatchedMacroEnv(object):
         """Start an episode from ``obs0`` (copied)."""
         self._cur = 0
         self._bufs[0].copy_(obs0)
+        if self.obs16 is not None:
+            self.obs16.copy_(obs0)
         self.t = 0
         return self.obs
 
@@ -62,7 +68,7 @@ class BatchedMacroEnv(object):
             (self.n_envs, self.n_cells, dtype_name(self.dtype), self.model.device, False),
             self.engine)
         src, dst = self._bufs[self._cur], self._bufs[1 - self._cur]
-        self.engine.step(src, dst, action=action, reward=self.reward)
+        self.engine.step(src, dst, action=action, reward=self.reward, obs16=self.obs16)
         self._cur = 1 - self._cur
         self.t += 1
         return self.obs, self.reward, self.t >= self.horizon, {}
@@ -100,6 +106,21 @@ class FeedForwardActor(nn.Module):
         x = self.net(obs.to(self.net[0].weight.dtype))
         return (0.5 * self.v_max_max) * (torch.tanh(x.squeeze(-1)) + 1.0)
 
+    def act_bf16(self, obs16, action_out):
+        """The same policy for a bfloat16 network and a bfloat16 observation
+        (``BatchedMacroEnv(obs_bf16=True).obs16``), written into
+        ``action_out`` (``(B,)`` in the engine dtype): hidden layers as GEMMs
+        with bias + ReLU in their epilogue, the output layer with its tanh and
+        scaling as one small kernel (``mt_actor_head``) -- no cast of the
+        observation, no elementwise kernels in between."""
+        from mbrl_traffic_b200.engine import actor_head
+        x = obs16
+        linears = [m for m in self.net if isinstance(m, nn.Linear)]
+        for lin in linears[:-1]:
+            x = torch._addmm_activation(lin.bias, x, lin.weight.t())   # relu(x W^T + b)
+        last = linears[-1]
+        return actor_head(x, last.weight, last.bias, action_out, 0.5 * self.v_max_max)
+
 
 class PolicyRollout(object):
     """``actor`` rolled through ``env``, captured ONCE as a CUDA graph of two
@@ -112,13 +133,21 @@ class PolicyRollout(object):
     def __init__(self, env, actor):
         self.env, self.actor = env, actor
         self.total = torch.zeros(env.n_envs, dtype=env.dtype, device=env.device)
+        self.action = torch.empty(env.n_envs, dtype=env.dtype, device=env.device)
+        #: the fused path: bfloat16 actor on the bfloat16 observation the step
+        #: kernel leaves behind (BatchedMacroEnv(obs_bf16=True))
+        self.fused = (env.obs16 is not None and hasattr(actor, "act_bf16")
+                      and next(actor.parameters()).dtype == torch.bfloat16)
         self.stream = torch.cuda.Stream(device=env.device)
         self.graph = None
 
     def _one(self):
         env = self.env
         with torch.no_grad():
-            act = self.actor(env.obs).to(env.dtype).contiguous()
+            if self.fused:
+                act = self.actor.act_bf16(env.obs16, self.action)
+            else:
+                act = self.actor(env.obs).to(env.dtype).contiguous()
         _, r, _, _ = env.step(act)
         self.total.add_(r)
 

@@ -118,3 +118,49 @@ def test_f32_lwr_is_pinned_over_10_steps_only():
     # NumPy float32: max 8.1e-6 after 10 steps
     assert _rel_err(got, ref).max() <= 3e-5
     m.close()
+
+
+@pytest.mark.parametrize("kind", ["arz", "lwr"])
+def test_trajectory_keeps_every_frame_on_the_device(kind, tmp_path):
+    """FiniteVolumeModel.trajectory / io.rollout_to_csv (the frame-keeping
+    loop of evaluate_model.py:388-414): every frame equals the oracle chain's,
+    for a batch, for one road, from NumPy and from a device tensor; the CSV
+    written from it reads back to the same numbers."""
+    _need_gpu()
+    from mbrl_traffic_b200 import io as mt_io
+    steps, b, n = 40, 5, 30
+    obs = make_obs(11, b=b, n=n)
+    m = make_model(kind)
+    frames = [obs]
+    for _ in range(steps):
+        frames.append(oracle_chain(kind, frames[-1], 1))
+    ref = np.stack(frames)
+    got = m.trajectory(obs, n_steps=steps)
+    assert isinstance(got, np.ndarray) and got.shape == (steps + 1, b, 2 * n)
+    assert np.array_equal(got, ref)
+    dev = m.trajectory(torch.as_tensor(obs, device="cuda:0"), n_steps=steps)
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), ref)
+    one = m.trajectory(obs[2], n_steps=steps)
+    assert one.shape == (steps + 1, 2 * n) and np.array_equal(one, ref[:, 2])
+    path = str(tmp_path / "run.csv")
+    times, out = mt_io.rollout_to_csv(m, obs[2], steps, path)
+    assert np.array_equal(out, ref[:, 2])
+    t2, back = mt_io.read_macro_csv(path)
+    np.testing.assert_allclose(back, ref[:, 2], rtol=1e-15, atol=0)
+    np.testing.assert_allclose(t2, np.arange(steps + 1) * 0.5)
+    m.close()
+
+
+def test_trajectory_with_per_step_speed_limits():
+    _need_gpu()
+    steps, b, n = 12, 7, 100
+    obs = make_obs(12, b=b, n=n)
+    rng = np.random.default_rng(5)
+    acts = rng.uniform(15, 30, (steps, b))
+    m = make_model("arz", action_is_speed_limit=True)
+    got = m.trajectory(obs, actions=acts, n_steps=steps)
+    ref = obs
+    for k in range(steps):
+        ref = o.arz_step(ref, v_max=acts[k], rho_crit=0.5)
+        assert np.array_equal(got[k + 1], ref), k
+    m.close()

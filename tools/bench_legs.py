@@ -86,6 +86,7 @@ def timed_replays(ctx, graph, reps, stream):
         e1 = torch.cuda.Event(enable_timing=True)
         ctx.barrier()
         with torch.cuda.stream(stream):
+            graph.replay()                      # untimed: the GPU idled at the barrier
             e0.record(stream)
             graph.replay()
             e1.record(stream)
@@ -161,7 +162,8 @@ def leg_rollout(ctx, args):
     model = ARZModel(None, None, None, None, 0, optimizer_cls=None,
                      action_is_speed_limit=True, device=ctx.local_rank, **p)
     obs = torch.as_tensor(make_obs(b, n, 200 + ctx.rank), device=ctx.dev)
-    env = BatchedMacroEnv(model, b, n, horizon=horizon, dtype=torch.float64)
+    env = BatchedMacroEnv(model, b, n, horizon=horizon, dtype=torch.float64,
+                          obs_bf16=not args.rollout_plain)
     torch.manual_seed(1)          # (a seed whose random-init actor keeps the scheme stable)
     actor = FeedForwardActor(2 * n).to(ctx.dev).to(torch.bfloat16)
     runner = PolicyRollout(env, actor)     # captured once, replayed for every rollout
@@ -187,6 +189,9 @@ def leg_rollout(ctx, args):
               "road_steps_per_s": ctx.world * b * horizon / sec,
               "n_gpus": ctx.world, "seconds": sec, "us_per_step": sec / horizon * 1e6,
               "scaling": "weak", "returns_finite": finite, "reps": 3,
+              "policy_path": "bf16 observation written by the step kernel, GEMMs with bias+ReLU "
+                             "epilogues, fused output layer" if runner.fused else
+                             "actor on the f64 observation (cast + eager layers)",
               "timed": "actor forward + model step + reward, two steps per CUDA-graph replay"})
     model.close()
 
@@ -271,6 +276,8 @@ def main():
     ap.add_argument("--nonlocal-steps", type=int, default=40)
     ap.add_argument("--rollout-envs", type=int, default=4096)
     ap.add_argument("--horizon", type=int, default=500)
+    ap.add_argument("--rollout-plain", action="store_true",
+                    help="rollout leg without the fused policy path (A/B)")
     ap.add_argument("--road-cells", type=int, default=10_000_000)
     ap.add_argument("--road-steps", type=int, default=256)
     ap.add_argument("--halo", type=int, default=8)
