@@ -82,14 +82,13 @@ def measured_peak():
 
 
 def csrc_hash():
-    """sha256 over the CUDA sources and the ABI header (sorted by name)."""
+    """sha256 over the sources the headline kernel is compiled from
+    (mt::step_pipe_kernel<double, ARZ>: mt_pipe.cuh and the physics headers)."""
     h = hashlib.sha256()
     d = os.path.join(ROOT, "mbrl_traffic_b200", "csrc")
-    files = sorted(os.path.join(d, f) for f in os.listdir(d)) + \
-        [os.path.join(ROOT, "include", "mtraffic.h")]
-    for path in files:
-        with open(path, "rb") as f:
-            h.update(os.path.basename(path).encode() + b"\0" + f.read())
+    for name in ("mt_cell.cuh", "mt_math.cuh", "mt_pipe.cuh"):
+        with open(os.path.join(d, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
     return h.hexdigest()[:16]
 
 

@@ -115,12 +115,24 @@ enum {
                              start early when its input lies outside them;
                              a chained step (input = previous output) waits
                              as before.                                    */
-  MT_FLAG_DEPENDENT_INPUT = 8
+  MT_FLAG_DEPENDENT_INPUT = 8,
                           /* every step waits for the launch before it
                              (turns the automatic check above off; for A/B
                              measurements, or when another library enqueues
                              programmatic-dependent kernels that write this
                              engine's inputs between its steps)            */
+  MT_FLAG_FSOLVE_ABORT = 16
+                          /* ARZ: mimic the reference on roads whose
+                             relaxation system it cannot solve.  With an
+                             exact-zero density rhs is NaN (arz.py:411,
+                             460), scipy's fsolve returns its initial guess
+                             (arz.py:462-463) and y stays frozen for the
+                             WHOLE road that step.  Off: the closed-form
+                             root is used everywhere (NaN at the affected
+                             cells only).  On: one more kernel per step
+                             re-reads the input, finds such roads and
+                             rewrites their speeds; multi-step launches are
+                             split into single steps.                      */
 };
 
 /* Fixed for the life of an engine. */

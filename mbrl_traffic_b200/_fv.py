@@ -27,7 +27,8 @@ class FiniteVolumeModel(Model):
     _param_names = ("rho_max", "v_max", "lam")
 
     def __init__(self, sess, ob_space, ac_space, replay_buffer, verbose,
-                 device=0, action_is_speed_limit=False, fast_math=False):
+                 device=0, action_is_speed_limit=False, fast_math=False,
+                 fsolve_abort=False):
         super(FiniteVolumeModel, self).__init__(
             sess=sess, ob_space=ob_space, ac_space=ac_space,
             replay_buffer=replay_buffer, verbose=verbose)
@@ -39,6 +40,10 @@ class FiniteVolumeModel(Model):
         self.action_is_speed_limit = action_is_speed_limit
         #: allow FMA contraction / approximate division (not bit-comparable)
         self.fast_math = fast_math
+        #: ARZ only: mimic the reference on roads with an exact-zero density,
+        #: where its fsolve call gives up and the relative flow stays frozen
+        #: for the whole road (arz.py:411, 460-463; MT_FLAG_FSOLVE_ABORT)
+        self.fsolve_abort = fsolve_abort
         self._engines = {}
         self._param_keys = {}
         self._pop_cache = {}
@@ -97,7 +102,7 @@ class FiniteVolumeModel(Model):
     def _sync_params(self, key, eng):
         values = self._param_values()
         snap = tuple((k, self._snapshot(v)) for k, v in sorted(values.items()))
-        snap += (("fast", self.fast_math),)
+        snap += (("fast", self.fast_math), ("abort", self.fsolve_abort))
         if self._param_keys.get(key) == snap:
             return
         kw = {}
@@ -109,7 +114,8 @@ class FiniteVolumeModel(Model):
                     device="cuda:%d" % self.device)
             kw[name] = value
         stream = None if any(_is_torch(v) for v in kw.values()) else 0
-        eng.set_params(fast_math=self.fast_math, stream=stream, **kw)
+        eng.set_params(fast_math=self.fast_math, fsolve_abort=self.fsolve_abort,
+                       stream=stream, **kw)
         self._param_keys[key] = snap
 
     # ------------------------------------------------------------------ #
@@ -315,7 +321,7 @@ class FiniteVolumeModel(Model):
                 .repeat_interleave(b).contiguous()
         if "gamma" in kw and isinstance(kw["gamma"], np.ndarray):
             kw["gamma"] = torch.as_tensor(kw["gamma"], device=dev).to(tdt)
-        eng.set_params(fast_math=self.fast_math, **kw)
+        eng.set_params(fast_math=self.fast_math, fsolve_abort=self.fsolve_abort, **kw)
         eng.step(ws["s"], ws["pred"])
         eng.density_sqerr(ws["pred"], ws["t"], ws["sq"])
         return (ws["sq"].view(p, b).sum(dim=1) / (b * n)).double().cpu().numpy()

@@ -20,6 +20,7 @@ MT_FLAG_FAST_MATH = 1
 MT_FLAG_NO_PIPELINE = 2
 MT_FLAG_INDEPENDENT_INPUT = 4
 MT_FLAG_DEPENDENT_INPUT = 8
+MT_FLAG_FSOLVE_ABORT = 16
 
 # every symbol include/mtraffic.h declares
 EXPORTS = (

@@ -21,6 +21,7 @@
 #include "mt_direct.cuh"
 #include "mt_nonlocal.cuh"
 #include "mt_aggregate.cuh"
+#include "mt_abort.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -715,6 +716,7 @@ bool segfused_geometry(const mt_engine* e, const void* obs_in, const void* obs_o
   const mt_params& p = e->params;
   const int N = (int)e->cfg.n_cells;
   if (e->cfg.model == MT_MODEL_NONLOCAL || (p.flags & MT_FLAG_NO_PIPELINE)) return false;
+  if (e->cfg.model == MT_MODEL_ARZ && (p.flags & MT_FLAG_FSOLVE_ABORT)) return false;
   if (p.bc_left == MT_BC_LOOP || p.bc_right == MT_BC_LOOP) return false;
   const bool aligned = (((uintptr_t)obs_in | (uintptr_t)obs_out) & 15u) == 0;
   const Geometry g = plan(e->cfg.n_envs, N, V, aligned);
@@ -1067,11 +1069,48 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
 // roads that fit one tile, 16-byte aligned buffers.
 bool can_fuse_steps(const mt_engine* e, const void* obs_in, const void* obs_out) {
   if (e->cfg.model == MT_MODEL_NONLOCAL || (e->params.flags & MT_FLAG_NO_PIPELINE)) return false;
+  // the reference's abort rule needs a look at every step's input (mt_abort.cuh)
+  if (e->cfg.model == MT_MODEL_ARZ && (e->params.flags & MT_FLAG_FSOLVE_ABORT)) return false;
   const int V = (int)(16 / e->elt);
   const bool aligned = (((uintptr_t)obs_in | (uintptr_t)obs_out) & 15u) == 0;
   const Geometry g = plan(e->cfg.n_envs, (int)e->cfg.n_cells, V, aligned);
   const char* off = getenv("MT_NO_FUSE");
   return g.vector_ok && g.tiles == 1 && !(off && off[0] == '1');
+}
+
+// MT_FLAG_FSOLVE_ABORT (mt_abort.cuh): after the step, roads whose relaxation
+// system the reference could not solve get the reference's result
+template <typename T>
+int abort_fixup(mt_engine* e, const void* obs_in, const void* action, void* obs_out,
+                void* reward_out, uint16_t* obs16, long long env0, long long n_env,
+                cudaStream_t stream) {
+  const mt_params& p = e->params;
+  const long long N = e->cfg.n_cells;
+  AbortArgs<T> a;
+  a.in = (const T*)obs_in + env0 * 2 * N;
+  a.out = (T*)obs_out + env0 * 2 * N;
+  a.table = (const T*)e->table + env0 * TBL_STRIDE;
+  a.flags = e->flags + env0;
+  a.action = action ? (const T*)action + env0 : nullptr;
+  a.reward = reward_out ? (T*)reward_out + env0 : nullptr;
+  a.obs16 = obs16 ? obs16 + env0 * 2 * N : nullptr;
+  a.aborted = nullptr;
+  a.B = n_env;
+  a.N = (int)N;
+  a.bc.bc_l = p.bc_left; a.bc.bc_r = p.bc_right;
+  a.bc.bl0 = (T)p.bc_left_val[0]; a.bc.bl1 = (T)p.bc_left_val[1];
+  a.bc.br0 = (T)p.bc_right_val[0]; a.bc.br1 = (T)p.bc_right_val[1];
+  a.step = (T)(p.dt / p.dx);
+  a.dt = (T)p.dt;
+  a.tau_scalar = (T)p.tau;
+  a.tau_env = p.tau_env ? (const T*)p.tau_env + env0 : nullptr;
+  const int wpb = 8;
+  const long long grid = (n_env + wpb - 1) / wpb;
+  if (grid > 0x7fffffffLL) return fail(MT_EINVAL, "batch too large for one launch");
+  arz_abort_fixup_kernel<T><<<(unsigned)grid, wpb * 32, 0, stream>>>(a);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return MT_OK;
 }
 
 int step_range(mt_engine* e, const void* obs_in, const void* action, void* obs_out,
@@ -1085,20 +1124,29 @@ int step_range(mt_engine* e, const void* obs_in, const void* action, void* obs_o
                           action_stride, reward_stride);
   uint16_t* const obs16 = e->obs16;
   e->obs16 = nullptr;
-  if (rc != MT_OK || obs16 == nullptr || e->obs16_written) return rc;
-  // this batch did not take the kernel that writes the copy itself
-  const long long row = 2LL * e->cfg.n_cells, n = n_env * row;
-  const int block = 256;
-  const long long grid = (n / 4 + block) / block;
-  if (grid > 0x7fffffffLL) return fail(MT_EINVAL, "batch too large for one launch");
-  if (e->cfg.dtype == MT_F64)
-    obs_to_bf16_kernel<double><<<(unsigned)grid, block, 0, stream>>>(
-        (const double*)obs_out + env0 * row, obs16 + env0 * row, n);
-  else
-    obs_to_bf16_kernel<float><<<(unsigned)grid, block, 0, stream>>>(
-        (const float*)obs_out + env0 * row, obs16 + env0 * row, n);
-  e->launches++;
-  CUDA_TRY(cudaGetLastError());
+  if (rc != MT_OK) return rc;
+  const long long row = 2LL * e->cfg.n_cells;
+  if (obs16 != nullptr && !e->obs16_written) {
+    // this batch did not take the kernel that writes the copy itself
+    const long long n = n_env * row;
+    const int block = 256;
+    const long long grid = (n / 4 + block) / block;
+    if (grid > 0x7fffffffLL) return fail(MT_EINVAL, "batch too large for one launch");
+    if (e->cfg.dtype == MT_F64)
+      obs_to_bf16_kernel<double><<<(unsigned)grid, block, 0, stream>>>(
+          (const double*)obs_out + env0 * row, obs16 + env0 * row, n);
+    else
+      obs_to_bf16_kernel<float><<<(unsigned)grid, block, 0, stream>>>(
+          (const float*)obs_out + env0 * row, obs16 + env0 * row, n);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  if ((e->params.flags & MT_FLAG_FSOLVE_ABORT) && e->cfg.model == MT_MODEL_ARZ && n_inner == 1) {
+    const int rc2 = e->cfg.dtype == MT_F64
+        ? abort_fixup<double>(e, obs_in, action, obs_out, reward_out, obs16, env0, n_env, stream)
+        : abort_fixup<float>(e, obs_in, action, obs_out, reward_out, obs16, env0, n_env, stream);
+    if (rc2 != MT_OK) return rc2;
+  }
   return MT_OK;
 }
 

@@ -127,7 +127,7 @@ class Engine(object):
     def set_params(self, dx, dt, rho_max, v_max, lam, boundary_conditions,
                    tau=1.0, rho_crit=None, gamma=None, fast_math=False,
                    no_pipeline=False, independent_input=False, dependent_input=False,
-                   scheme="godunov", alpha=None, stream=None):
+                   scheme="godunov", alpha=None, fsolve_abort=False, stream=None):
         """``mt_set_params``.  rho_max / v_max / tau / lam / rho_crit may be
         Python scalars or device tensors of shape (n_envs,) in the engine
         dtype; ``gamma`` is a device tensor of look-ahead weights."""
@@ -173,7 +173,8 @@ class Engine(object):
         p.flags = (_lib.MT_FLAG_FAST_MATH if fast_math else 0) | \
             (_lib.MT_FLAG_NO_PIPELINE if no_pipeline else 0) | \
             (_lib.MT_FLAG_INDEPENDENT_INPUT if independent_input else 0) | \
-            (_lib.MT_FLAG_DEPENDENT_INPUT if dependent_input else 0)
+            (_lib.MT_FLAG_DEPENDENT_INPUT if dependent_input else 0) | \
+            (_lib.MT_FLAG_FSOLVE_ABORT if fsolve_abort else 0)
         _lib.check(self._lib.mt_set_params(self._h, ctypes.byref(p),
                                            _stream_ptr(stream)))
         self._keep = keep

@@ -180,7 +180,7 @@ def arz_compute_flux(rho, y, v_max, rho_max, lam, rho_crit):
 
 
 def arz_step(obs, dx=50, dt=0.5, rho_max=1, v_max=30, tau=9, lam=1,
-             boundary_conditions="loop", rho_crit=None):
+             boundary_conditions="loop", rho_crit=None, fsolve_abort=False):
     """``ARZModel.get_next_obs`` for a batch (arz.py:205-221).
 
     Relaxation.  The reference solves ``F(z) = z + (dt/tau) *
@@ -199,8 +199,13 @@ def arz_step(obs, dx=50, dt=0.5, rho_max=1, v_max=30, tau=9, lam=1,
     because the reference freezes it at construction (arz.py:199).
 
     Domain: rho > 0 everywhere.  An exact zero density makes ``P`` NaN here
-    (0/0, arz.py:411); the reference's fsolve then aborts and returns its
-    initial guess for the whole road, which this closed form does not mimic.
+    (0/0, arz.py:411) and with it ``rhs`` (arz.py:460); every residual fsolve
+    then sees is NaN, MINPACK rejects every trial step and hands back its
+    initial guess ``x0 = y`` for the WHOLE road (the system is solved jointly,
+    arz.py:462-463) -- the density still advances.  ``fsolve_abort=True``
+    mimics that: a road whose ``rhs`` holds a non-finite value in ANY of its N
+    cells keeps ``y' = y`` [checked against the unmodified reference:
+    tests/golden, cases ``arz_zero_*``].
     """
     rho, v, squeeze = _split(obs)
     if rho_crit is None:
@@ -213,6 +218,12 @@ def arz_step(obs, dx=50, dt=0.5, rho_max=1, v_max=30, tau=9, lam=1,
     # arz.py:456 and the closed-form root; interior cells only (arz.py:464-465)
     rho_new = rho + (step * (qm - q))
     y_new = (y + (step * (pm - p))) / (1 + dt / _col(tau))
+    if fsolve_abort:
+        with np.errstate(invalid="ignore", over="ignore"):
+            rhs = y + (step * (pm - p)) + (dt / _col(tau)) * (
+                rho_new * v_eq(rho_new, v_max, rho_max, lam))      # arz.py:460-461
+        aborted = ~np.isfinite(rhs).all(axis=1)
+        y_new = np.where(aborted[:, None], y, y_new)
     rho_in = rho_new[:, 1:-1]
     y_in = y_new[:, 1:-1]
 

@@ -122,7 +122,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     with open(os.path.join(ROOT, "include", "mtraffic.h")) as f:
         header = f.read()
-    declared = set(re.findall(r"\b(mt_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(mt_[a-z_0-9]+)\s*\(", header))
     assert declared == set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name

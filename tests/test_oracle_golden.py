@@ -6,6 +6,8 @@ tests/golden were produced by executing the unmodified reference
 (oracle/make_golden.py).  Bars: LWR bit-equal; ARZ density half bit-equal after
 one step, velocity half within 1e-12 relative (fsolve noise).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -156,3 +158,33 @@ def test_oracle_against_live_reference():
     out = o.arz_step(obs)
     assert np.array_equal(ref[:n], out[:n])
     np.testing.assert_allclose(ref[n:], out[n:], rtol=1e-12)
+
+
+# --------------------------------------------------------------------------- #
+# exact-zero densities: the reference's fsolve gives up (arz.py:411, 460-463)  #
+# --------------------------------------------------------------------------- #
+def _zero_cases():
+    import json
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                        "reference_zero_density.npz")
+    z = np.load(path)
+    for key in sorted(set(k.split("/")[0] for k in z.files)):
+        yield key, z[key + "/obs"], z[key + "/out1"], json.loads(str(z[key + "/meta"]))
+
+
+def test_oracle_mimics_the_reference_on_roads_with_an_exact_zero_density():
+    """88 outputs of the unmodified reference (oracle/make_golden_zero.py): a
+    road with rho == 0 somewhere keeps its relative flow for that step."""
+    n_abort = 0
+    for key, obs, ref, meta in _zero_cases():
+        p, n = meta["params"], meta["n"]
+        kw = dict(dx=p["dx"], dt=p["dt"], rho_max=p["rho_max"], v_max=p["v_max"], tau=p["tau"],
+                  lam=p["lam"], boundary_conditions=p["boundary_conditions"])
+        got = o.arz_step(obs, fsolve_abort=True, **kw)
+        assert np.isfinite(ref).all(), key           # the reference never returns NaN here
+        assert np.array_equal(got[:n], ref[:n]), key
+        np.testing.assert_allclose(got[n:], ref[n:], rtol=1e-12, atol=0, err_msg=key)
+        plain = o.arz_step(obs, **kw)
+        if not np.array_equal(plain, got, equal_nan=True):
+            n_abort += 1
+    assert n_abort >= 40          # most cases do exercise the abort rule
