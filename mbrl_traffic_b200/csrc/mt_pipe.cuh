@@ -303,6 +303,11 @@ template <typename T> struct PipeArgs {
   // mt_step_obs16: a bfloat16 copy of the new state, (B, 2N) row-major, for a
   // policy network that reads the observation next (nullptr: none)
   uint16_t* obs16 = nullptr;
+  // Rewards of roads wider than a warp, static schedule: the CTA is launched
+  // with one more warp (288 threads are allocated as 10 warps anyway) that adds
+  // up the per-thread sums the consumers leave in shared memory; the input ring
+  // gives up its last stage for them.
+  int reducer = 0;
 };
 
 // Which instantiations of step_pipe_kernel draw their tiles from a counter.
@@ -323,8 +328,13 @@ template <typename T, int MODEL, bool FAST> struct PipeDynamic {
 // U: 16-byte vectors (of each field) per thread; a thread owns U*V cells.
 // (288 threads are allocated as 10 warps: 96 registers per thread is what two
 // CTAs per SM leave; a build with __maxnreg__(112) ran one CTA per SM, 35 us)
-template <typename T, int MODEL, bool FAST, int LAMK, bool UNIFORM, int U>
-__global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kernel(const PipeArgs<T> a) {
+// REDUCER: the instantiation launched with the extra reducer warp (rewards of
+// roads wider than a warp under the static schedule).  A separate instantiation
+// so that the plain step keeps its compile-time stage count and its code: with
+// the choice made at run time the headline step went from 23.0 to 26.2 us.
+template <typename T, int MODEL, bool FAST, int LAMK, bool UNIFORM, int U, bool REDUCER = false>
+__global__ void __launch_bounds__(PIPE_BLOCK / U + (REDUCER ? 64 : 32), PIPE_CTAS)
+step_pipe_kernel(const PipeArgs<T> a) {
   constexpr int V = Vec<T>::N;
   constexpr int CPT = U * V;
   constexpr bool ARZ = (MODEL == 1);
@@ -348,6 +358,12 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
   const uint32_t full0 = smem_u32(&sm.full[0]), empty0 = smem_u32(&sm.empty[0]);
   const uint32_t ofull0 = smem_u32(&sm.out_full[0]), ofree0 = smem_u32(&sm.out_free[0]);
 
+  // reducer warp on: the last input stage holds the consumers' (sum rho v, sum rho) pairs
+  static_assert(!REDUCER || !DYN, "the reducer warp follows the static tile schedule");
+  constexpr bool reducer_on = REDUCER;   // (the host launches it only with rewards and tpe > 32)
+  constexpr int n_stages = REDUCER ? PIPE_STAGES - 1 : PIPE_STAGES;
+  T* const pairbuf = reinterpret_cast<T*>(sm.in[PIPE_STAGES - 1]);   // [PIPE_OUT][NC][2]
+
   if (t == 0) MT_STAMP(0);
 #ifdef MT_TRACE
   if (t == 0 && a.trace) {
@@ -367,7 +383,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
     }
     for (int o = 0; o < PIPE_OUT; ++o) {
       mbar_init(&sm.out_full[o], (uint32_t)(NC >> 5));
-      mbar_init(&sm.out_free[o], 1);
+      mbar_init(&sm.out_free[o], reducer_on ? 2u : 1u);   // the store drained (+ the pairs summed)
     }
     fence_mbar_init();
   }
@@ -430,7 +446,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
       // adds them up in warp order and stores the quotient, so the consumers
       // need no second barrier per tile.
       auto finish_rewards = [&](int o, int tile) {
-        if (a.reward == nullptr || a.tpe <= 32) return;
+        if (a.reward == nullptr || a.tpe <= 32 || reducer_on) return;
         const int envs = tile == last_tile ? last_envs : a.epc;
         const int nw = a.tpe >> 5;
         for (int el = 0; el < envs; ++el) {
@@ -442,7 +458,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
       if constexpr (!DYN) {
         auto issue_load = [&](int i) {
           const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-          const int s = i % PIPE_STAGES;
+          const int s = i % n_stages;
           const int envs = tile == last_tile ? last_envs : a.epc;
           const uint32_t tbl = tbl_bytes_of(envs);
           if (ARZ) {
@@ -473,18 +489,18 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
                                row_bytes >> 1);
           }
         };
-        const int pre = n_my < PIPE_STAGES ? n_my : PIPE_STAGES;
+        const int pre = n_my < n_stages ? n_my : n_stages;
         for (int i = 0; i < pre; ++i) issue_load(i);
         const int ahead = a.l2_ahead;
-        for (int i = PIPE_STAGES; i < PIPE_STAGES + ahead && i < n_my; ++i) prefetch(i);
+        for (int i = n_stages; i < n_stages + ahead && i < n_my; ++i) prefetch(i);
         if (early) pdl_wait_prior_grid();   // before the first store
         for (int i = 0; i < n_my; ++i) {
           const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-          const int s = i % PIPE_STAGES, o = i % PIPE_OUT;
-          if (ahead > 0 && i + PIPE_STAGES + ahead < n_my) prefetch(i + PIPE_STAGES + ahead);
-          if (i + PIPE_STAGES < n_my) {  // refill stage s once the consumers have read tile i
-            mbar_wait_relaxed(empty0 + 8 * s, (uint32_t)((i / PIPE_STAGES) & 1), PRODUCER_NAP_NS);
-            issue_load(i + PIPE_STAGES);
+          const int s = i % n_stages, o = i % PIPE_OUT;
+          if (ahead > 0 && i + n_stages + ahead < n_my) prefetch(i + n_stages + ahead);
+          if (i + n_stages < n_my) {  // refill stage s once the consumers have read tile i
+            mbar_wait_relaxed(empty0 + 8 * s, (uint32_t)((i / n_stages) & 1), PRODUCER_NAP_NS);
+            issue_load(i + n_stages);
           }
           mbar_wait_relaxed(ofull0 + 8 * o, (uint32_t)((i / PIPE_OUT) & 1), PRODUCER_NAP_NS);
           bulk_store(gout + (size_t)tile * tile_bytes, out0 + (uint32_t)o * PIPE_TILE_BYTES,
@@ -596,6 +612,39 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
       }
       bulk_wait_read<0>();  // shared memory must outlive the last bulk store
       MT_STAMP(6);
+    }
+    if constexpr (REDUCER) {
+      if (t >= NC + 32) {
+        // ===================== reducer warp ================================
+        // Per tile and road: each lane adds the pairs of the road's threads
+        // lane, lane + 32, ... in that order, a butterfly adds the lanes, lane
+        // 0 stores sum(rho v) / sum(rho).  A fixed order; the consumers are
+        // spared the butterfly (10 shuffles and their selects per thread).
+        const int lane = t & 31;
+        const unsigned full = 0xffffffffu;
+        if (early) pdl_wait_prior_grid();   // before the first reward is stored
+        for (int i = 0; i < n_my; ++i) {
+          const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+          const int o = i % PIPE_OUT;
+          const int envs = tile == last_tile ? last_envs : a.epc;
+          mbar_wait(ofull0 + 8 * o, (uint32_t)((i / PIPE_OUT) & 1));
+          for (int el = 0; el < envs; ++el) {
+            const T* pr = pairbuf + 2 * (o * NC + el * a.tpe);
+            T n = 0, d = 0;
+            for (int k = lane; k < a.tpe; k += 32) {
+              n += pr[2 * k];
+              d += pr[2 * k + 1];
+            }
+            const bool odd = (lane & 1) != 0;
+            T acc = (odd ? d : n) + __shfl_xor_sync(full, odd ? n : d, 1);
+            for (int off = 2; off <= 16; off <<= 1) acc += __shfl_xor_sync(full, acc, off);
+            const T dsum = __shfl_sync(full, acc, 1);
+            if (lane == 0) a.reward[(size_t)tile * a.epc + el] = acc / dsum;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ofree0 + 8 * o);   // the pairs of stage o are summed
+        }
+      }
     }
     return;
   }
@@ -754,7 +803,12 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
         }
       }
     }
-    if (want_reward && a.tpe > 32) {
+    if constexpr (REDUCER) {
+      // my sums go to the reducer warp (all consumer threads store: idle ones zeros)
+      T* pr = pairbuf + 2 * (o * NC + t);
+      pr[0] = num;
+      pr[1] = den;
+    } else if (want_reward && a.tpe > 32) {
       // Per-road sum(rho v) / sum(rho), fixed order.  Shuffles are the cost of
       // this reduction (one warp-wide SHFL per clock and SM), so the two sums
       // share one butterfly: in the first round even lanes keep the numerator
@@ -783,7 +837,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_pipe_kern
       }
       if (active && row_first) a.reward[env] = num / den;
     }
-    if (++s == PIPE_STAGES) { s = 0; ph_in ^= 1; }
+    if (++s == n_stages) { s = 0; ph_in ^= 1; }
     if (++o == PIPE_OUT) { o = 0; ph_out ^= 1; }
   }
 }

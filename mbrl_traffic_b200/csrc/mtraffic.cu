@@ -23,6 +23,14 @@
 #include "mt_aggregate.cuh"
 #include "mt_abort.cuh"
 
+// defined in mt_pipe_arz64.cu
+namespace mt {
+#define MT_PIPE_ARZ64(K, UNI, U, R) \
+  extern template __global__ void step_pipe_kernel<double, 1, false, K, UNI, U, R>(const PipeArgs<double>);
+#include "mt_pipe_arz64.inc"
+#undef MT_PIPE_ARZ64
+}  // namespace mt
+
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -362,6 +370,16 @@ bool pipe_use_ring(bool is_f32, bool fast, bool arz, bool dynamic, bool uniform)
   return v != 0;
 }
 
+// MT_REWARD_REDUCER=0: rewards by the consumers' butterfly and the producer thread (A/B knob)
+bool pipe_reward_reducer() {
+  static int v = -1;
+  if (v < 0) {
+    const char* s = getenv("MT_REWARD_REDUCER");
+    v = (s && s[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 // MT_TABLE_STAGE=0: the pipelined kernel's consumers read their table rows from
 // global memory instead of a copy staged with the tile (A/B knob)
 bool pipe_stage_table() {
@@ -422,6 +440,20 @@ int launch_pipe(const PipeArgs<T>& pa, int grid, cudaStream_t stream) {
   if (pa.n_inner > 1)
     return launch_pdl(step_fused_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>, pa, grid,
                       pa.nc + 32, sizeof(PipeSmem<T, U>), stream);
+  if constexpr (MODEL == 1 && sizeof(T) == 8 && !FAST) {
+    if (pa.reducer) {   // one more warp adds up the rewards (mt_pipe.cuh)
+      static bool red_dev[MAX_DEVICES] = {};
+      bool* rf = configured_flag(red_dev);
+      if (rf == nullptr || !*rf) {
+        CUDA_TRY(cudaFuncSetAttribute(step_pipe_kernel<T, MODEL, FAST, LAMK, UNIFORM, U, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(PipeSmem<T, U>)));
+        if (rf) *rf = true;
+      }
+      return launch_pdl(step_pipe_kernel<T, MODEL, FAST, LAMK, UNIFORM, U, true>, pa, grid,
+                        pa.nc + 64, sizeof(PipeSmem<T, U>), stream);
+    }
+  }
   return launch_pdl(step_pipe_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>, pa, grid,
                     pa.nc + 32, sizeof(PipeSmem<T, U>), stream);
 }
@@ -935,6 +967,10 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
     const bool is_ring = pipe_use_ring(sizeof(T) == 4, fast, e->cfg.model == MT_MODEL_ARZ,
                                        pa.sched != nullptr, e->uniform);
     pa.tbl_off = is_ring ? 0 : tbl_off;
+    // a reducer warp for the rewards of roads wider than a warp (static schedule)
+    // (ARZ f64 is the instantiation with the static schedule: PipeDynamic in mt_pipe.cuh)
+    pa.reducer = (reward_out != nullptr && pa.tpe > 32 && e->cfg.model == MT_MODEL_ARZ &&
+                  sizeof(T) == 8 && !is_ring && n_inner == 1 && pipe_reward_reducer()) ? 1 : 0;
     if (obs16 != nullptr && !is_ring && n_inner == 1) {
       pa.obs16 = obs16 + env0 * 2 * N;
       e->obs16_written = true;
