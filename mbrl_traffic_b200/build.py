@@ -26,11 +26,13 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "-I", os.path.join(ROOT, "include"),
 ]
-# ~300 kernels in the big translation unit: ptxas works on them in parallel.
-# NOT for mt_pipe_arz64.cu: split compilation changes the code of individual
-# kernels (the headline instantiation: 2248 instead of 2016 instructions, 89
-# instead of 96 registers, 25.0 instead of 23.0 us per step).
-SPLIT_FLAGS = {"mtraffic.cu": ["-split-compile", str(max(1, min(8, os.cpu_count() or 1)))]}
+# No `-split-compile`: it halves the build time of the big translation unit but
+# changes the code of individual kernels, differently for every thread count
+# (measured on one box, split 8 vs none: headline step 25.0 vs 23.0 us, ARZ f32
+# EXACT 0.71 vs 0.84 of the HBM peak, ARZ f32 FAST 0.87 vs 0.94, non-local 0.56
+# vs 0.62, fused 100-step rollout 1.96e11 vs 2.10e11): the library must not
+# depend on the number of cores of the machine that built it.
+SPLIT_FLAGS = {}
 
 
 def extra_flags():

@@ -9,9 +9,18 @@
 // experiments/evaluate_model.py:398-403 (and any rollout without a policy in
 // the loop) runs at the arithmetic rate of the chip instead of the bandwidth
 // rate.  Per-step speed limits are read as they are needed
-// (action[j * stride + road]); a reward is produced for the final step only.
+// (action[j * stride + road]); a reward row is produced for the final step or
+// for every step (mt_rollout with rewards: the K-shoot planner).
 // Kept apart from step_pipe_kernel so that the single-step kernel's code and
 // register allocation stay exactly as tuned.
+//
+// REDUCER (a reward row per step, roads wider than a warp, f64): the CTA gets
+// one more warp.  Each step the consumers leave their (sum rho v, sum rho) in
+// shared memory and arrive -- without waiting -- on a named barrier the reducer
+// warp sleeps on; it adds the road's pairs up in a fixed order and stores the
+// reward, then frees the (double-buffered) pair slots through an mbarrier.
+// The consumers are spared the per-step butterfly and the road's first warp
+// the per-step finish that used to sit on every step's critical path.
 #pragma once
 #include <stdint.h>
 #include "mtraffic.h"
@@ -21,12 +30,15 @@
 
 namespace mt {
 
-template <typename T, int MODEL, bool FAST, int LAMK, bool UNIFORM, int U>
-__global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_fused_kernel(const PipeArgs<T> a) {
+template <typename T, int MODEL, bool FAST, int LAMK, bool UNIFORM, int U, bool REDUCER = false>
+__global__ void __launch_bounds__(PIPE_BLOCK / U + (REDUCER ? 64 : 32), PIPE_CTAS)
+step_fused_kernel(const PipeArgs<T> a) {
   constexpr int V = Vec<T>::N;
   constexpr int CPT = U * V;
   constexpr bool ARZ = (MODEL == 1);
-  constexpr int PIPE_STAGES = PipeCfg<T, U>::STAGES;
+  constexpr int PIPE_STAGES_ALL = PipeCfg<T, U>::STAGES;
+  // the reducer's pair slots (and its mbarriers) take the last input stage
+  constexpr int PIPE_STAGES = REDUCER ? PIPE_STAGES_ALL - 1 : PIPE_STAGES_ALL;
   constexpr int PIPE_XCH = PipeCfg<T, U>::XCH;
   using A = Ar<T, FAST>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -45,6 +57,11 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_fused_ker
   const uint32_t full0 = smem_u32(&sm.full[0]), empty0 = smem_u32(&sm.empty[0]);
   const uint32_t ofull0 = smem_u32(&sm.out_full[0]), ofree0 = smem_u32(&sm.out_free[0]);
 
+  // REDUCER: [2][NC][2] sums, then two mbarriers "pairs of buffer b summed"
+  T* const pairbuf = reinterpret_cast<T*>(sm.in[PIPE_STAGES_ALL - 1]);
+  uint64_t* const rfree = reinterpret_cast<uint64_t*>(sm.in[PIPE_STAGES_ALL - 1] + PIPE_TILE_BYTES / 2);
+  const uint32_t rfree0 = smem_u32(rfree);
+
   pdl_launch_dependents();
   // pad slots of the exchange arrays stay zero for the kernel's life: they
   // feed the (discarded) left-face flux of each road's first cell
@@ -58,6 +75,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_fused_ker
       mbar_init(&sm.out_full[o], (uint32_t)(NC >> 5));
       mbar_init(&sm.out_free[o], 1);
     }
+    if constexpr (REDUCER) { mbar_init(&rfree[0], 1); mbar_init(&rfree[1], 1); }
     fence_mbar_init();
   }
   __syncthreads();
@@ -124,6 +142,39 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_fused_ker
       }
       bulk_wait_read<0>();  // shared memory must outlive the last bulk store
     }
+    if constexpr (REDUCER) {
+      if (t >= NC + 32) {
+        // ===================== reducer warp ================================
+        const int lane = t & 31;
+        const unsigned full = 0xffffffffu;
+        unsigned g = 0;   // steps seen so far (all tiles): buffer g & 1
+        for (int i = 0; i < n_my; ++i) {
+          const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+          const int envs = tile == last_tile ? last_envs : a.epc;
+          for (int j = 0; j < a.n_inner; ++j, ++g) {
+            const unsigned b = g & 1u;
+            // sleep until all NC consumer threads have left this step's pairs
+            asm volatile("bar.sync %0, %1;" ::"r"(2u + b), "r"(NC + 32) : "memory");
+            for (int el = 0; el < envs; ++el) {
+              const T* pr = pairbuf + 2 * ((int)b * NC + el * a.tpe);
+              T n = 0, d = 0;
+              for (int k = lane; k < a.tpe; k += 32) {
+                n += pr[2 * k];
+                d += pr[2 * k + 1];
+              }
+              const bool odd = (lane & 1) != 0;
+              T acc = (odd ? d : n) + __shfl_xor_sync(full, odd ? n : d, 1);
+              for (int off = 2; off <= 16; off <<= 1) acc += __shfl_xor_sync(full, acc, off);
+              const T dsum = __shfl_sync(full, acc, 1);
+              if (lane == 0)
+                a.reward[(size_t)j * (size_t)a.reward_stride + (size_t)tile * a.epc + el] = acc / dsum;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(rfree0 + 8 * b);   // buffer b may be overwritten
+          }
+        }
+      }
+    }
     return;
   }
 
@@ -149,6 +200,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_fused_ker
   int s = 0, o = 0, xpar = 0;
   uint32_t ph_in = 0, ph_out = 0;
   const int n_inner = a.n_inner;
+  unsigned gstep = 0;   // REDUCER: steps done so far (all tiles), as the reducer counts them
   for (int i = 0; i < n_my; ++i) {
     const int tile = (int)blockIdx.x + i * (int)gridDim.x;
     const int envs_here = tile == last_tile ? last_envs : a.epc;
@@ -242,7 +294,9 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_fused_ker
       consumer_sync(NC);                               // exchange visible
       if (j == 0 && lane0) mbar_arrive(empty0 + 8 * s);  // stage s fully read: release it
       if (last) mbar_wait(ofree0 + 8 * o, ph_out ^ 1);   // output stage drained by its last store
-      if (every && a.tpe > 32 && j > 0 && pos < 32) reward_finish(j - 1);
+      if constexpr (!REDUCER) {
+        if (every && a.tpe > 32 && j > 0 && pos < 32) reward_finish(j - 1);
+      }
 
       if (active) {
         const T S_right = xS[xi + 1], D_left = xD[xi], r_left = xR[xi];
@@ -281,7 +335,17 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_fused_ker
         }
         const unsigned full = 0xffffffffu;
         const int width = a.tpe <= 32 ? a.tpe : 32;
-        if (width >= 2) {
+        if constexpr (REDUCER) {
+          // hand my sums to the reducer warp: wait (normally not at all) until it
+          // has summed this buffer's previous contents, store, arrive without waiting
+          const unsigned b = gstep & 1u;
+          if (gstep >= 2) mbar_wait(rfree0 + 8 * b, ((gstep >> 1) - 1) & 1u);
+          T* pr = pairbuf + 2 * ((int)b * NC + t);
+          pr[0] = pn;
+          pr[1] = pd;
+          asm volatile("bar.arrive %0, %1;" ::"r"(2u + b), "r"(NC + 32) : "memory");
+          ++gstep;
+        } else if (width >= 2) {
           const bool odd = (t & 1) != 0;
           T acc = (odd ? pd : pn) + __shfl_xor_sync(full, odd ? pn : pd, 1);
           for (int off = 2; off < width; off <<= 1) acc += __shfl_xor_sync(full, acc, off);
@@ -304,9 +368,11 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, PIPE_CTAS) step_fused_ker
     __syncwarp();
     if (lane0) mbar_arrive(ofull0 + 8 * o);          // non-blocking hand-off to the producer
 
-    if (every && a.tpe > 32) {                       // the last step's reward row
-      consumer_sync(NC);
-      if (pos < 32) reward_finish(n_inner - 1);
+    if constexpr (!REDUCER) {
+      if (every && a.tpe > 32) {                       // the last step's reward row
+        consumer_sync(NC);
+        if (pos < 32) reward_finish(n_inner - 1);
+      }
     }
     if (want_reward && !every) {
       // per-road sum(rho v)/sum(rho) in a fixed order

@@ -356,17 +356,20 @@ bool auto_independent() {
 // the producer-warp kernel has (B200, 16384x1000 f32 EXACT: ARZ 82 % ring vs
 // 74 % pipe, LWR 79 % ring vs 91 % pipe of HBM peak).
 // MT_KERNEL=pipe|ring overrides for A/B runs.
-// A per-road parameter table costs ARZ f64 about 16 more live registers: the
-// producer-warp kernel is held to 96 per thread (288 threads are allocated as
-// 10 warps) and spills, the ring kernel (256 threads, 128 registers) does not
-// (4096 x 1000, lam = 1: 37 us vs 48 us per step).
+// (ARZ f64 with a per-road parameter table needs ~16 more live registers than
+// the 96 the producer-warp kernel is held to and spills 80-100 B; the ring kernel
+// has 128 and does not spill, yet measures slower in a build without split
+// compilation -- 4096 x 1000, lam = 1: pipe with staged table rows 38.7 us, pipe
+// reading the table from global memory 41.0 us, ring 43.4 us -- so such batches
+// stay with the pipelined kernel; `uniform` is kept for A/B builds.)
 bool pipe_use_ring(bool is_f32, bool fast, bool arz, bool dynamic, bool uniform) {
   static int v = -1;
   if (v < 0) {
     const char* s = getenv("MT_KERNEL");
     v = !s ? 2 : (s[0] == 'r') ? 1 : 0;
   }
-  if (v == 2) return (is_f32 && !fast && (arz || !dynamic)) || (!is_f32 && arz && !uniform);
+  (void)uniform;
+  if (v == 2) return is_f32 && !fast && (arz || !dynamic);
   return v != 0;
 }
 
@@ -437,9 +440,24 @@ int launch_pipe(const PipeArgs<T>& pa, int grid, cudaStream_t stream) {
   if (pa.n_inner == 1 && pipe_use_ring(sizeof(T) == 4, FAST, MODEL == 1, pa.sched != nullptr, UNIFORM))
     return launch_pdl(step_ring_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>, pa, grid, pa.nc,
                       sizeof(RingSmem<T, U>), stream);
-  if (pa.n_inner > 1)
+  if (pa.n_inner > 1) {
+    if constexpr (sizeof(T) == 8 && U == 2 && !FAST) {
+      if (pa.reducer) {   // a reward row per step: one more warp adds the sums up (mt_fused.cuh)
+        static bool red_dev[MAX_DEVICES] = {};
+        bool* rf = configured_flag(red_dev);
+        if (rf == nullptr || !*rf) {
+          CUDA_TRY(cudaFuncSetAttribute(step_fused_kernel<T, MODEL, FAST, LAMK, UNIFORM, U, true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)sizeof(PipeSmem<T, U>)));
+          if (rf) *rf = true;
+        }
+        return launch_pdl(step_fused_kernel<T, MODEL, FAST, LAMK, UNIFORM, U, true>, pa, grid,
+                          pa.nc + 64, sizeof(PipeSmem<T, U>), stream);
+      }
+    }
     return launch_pdl(step_fused_kernel<T, MODEL, FAST, LAMK, UNIFORM, U>, pa, grid,
                       pa.nc + 32, sizeof(PipeSmem<T, U>), stream);
+  }
   if constexpr (MODEL == 1 && sizeof(T) == 8 && !FAST) {
     if (pa.reducer) {   // one more warp adds up the rewards (mt_pipe.cuh)
       static bool red_dev[MAX_DEVICES] = {};
@@ -971,6 +989,10 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
     // (ARZ f64 is the instantiation with the static schedule: PipeDynamic in mt_pipe.cuh)
     pa.reducer = (reward_out != nullptr && pa.tpe > 32 && e->cfg.model == MT_MODEL_ARZ &&
                   sizeof(T) == 8 && !is_ring && n_inner == 1 && pipe_reward_reducer()) ? 1 : 0;
+    // ... and for a reward row per step of a fused rollout (f64, 4 cells per thread)
+    if (n_inner > 1 && reward_out != nullptr && reward_stride > 0 && pa.tpe > 32 &&
+        sizeof(T) == 8 && U == 2 && pipe_reward_reducer())
+      pa.reducer = 1;
     if (obs16 != nullptr && !is_ring && n_inner == 1) {
       pa.obs16 = obs16 + env0 * 2 * N;
       e->obs16_written = true;
