@@ -115,6 +115,15 @@ step_segfused_kernel(const SegFusedArgs<T> a) {
   auto locate = [&](int tile, int& env, int& j, int& w, int& vs, int& ve) {
     env = tile / TPR;
     j = tile - env * TPR;
+    // With a ghost-cell exchange folded in, the road's LAST window trades places
+    // with its second: both edge windows are then in the launch's first wave, so
+    // a rank's pushes are out long before its neighbours start the next launch
+    // (whose edge windows wait for exactly those flags) instead of at its very
+    // end.  Windows of one launch are independent: any order gives the same cells.
+    if (a.halo.push_epoch != 0u && TPR > 2) {
+      if (j == 1) j = TPR - 1;
+      else if (j == TPR - 1) j = 1;
+    }
     const bool last = (j == TPR - 1);
     w = last ? N - W : j * S;
     vs = (j == 0) ? 0 : a.hh + j * S;

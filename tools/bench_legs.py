@@ -280,7 +280,7 @@ def main():
                     help="rollout leg without the fused policy path (A/B)")
     ap.add_argument("--road-cells", type=int, default=10_000_000)
     ap.add_argument("--road-steps", type=int, default=256)
-    ap.add_argument("--halo", type=int, default=8)
+    ap.add_argument("--halo", type=int, default=16)
     args = ap.parse_args()
     ctx = Ctx()
     for name in args.legs.split(","):
