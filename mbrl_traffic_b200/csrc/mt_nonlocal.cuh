@@ -48,19 +48,21 @@ namespace mt {
 constexpr int NL_STAGES = 4;
 constexpr int NL_IN_BYTES = PIPE_TILE_BYTES / 2;   // densities of one tile (8 KB)
 constexpr int NL_MAX_ETA = 256;                    // look-ahead cells
-constexpr int NL_GHOSTS = 1024;                    // extra V(rho) slots per tile for ghosts
+constexpr int NL_GHOSTS = 320;                     // extra V(rho) slots per tile for ghosts
 
 template <typename T> struct NlSmem {
   static constexpr int VE = NL_IN_BYTES / (int)sizeof(T) + NL_GHOSTS + 64;
   alignas(128) unsigned char in[NL_STAGES][NL_IN_BYTES];
   alignas(128) unsigned char out[PIPE_OUT][PIPE_TILE_BYTES];
-  alignas(16) T ve[2][VE];          // V(rho) of the tile incl. ghosts, double-buffered
+  alignas(16) T ve[3][VE];          // V(rho) of the tile incl. ghosts: two buffers in turn, or
+                                    // three when tiles are published one ahead (AHEAD)
   T gamma[NL_MAX_ETA];
   T s_num[PIPE_BLOCK / 32], s_den[PIPE_BLOCK / 32];
   alignas(8) uint64_t full[NL_STAGES];
   uint64_t empty[NL_STAGES];
   uint64_t out_full[PIPE_OUT];
   uint64_t out_free[PIPE_OUT];
+  uint64_t pub[3];                  // AHEAD: every consumer warp has published buffer b
 };
 static_assert(sizeof(NlSmem<double>) <= 113 * 1024, "two CTAs per SM must fit in 227 KB");
 
@@ -90,8 +92,9 @@ __device__ __forceinline__ T nl_left_ghost(const BcArgs<T>& b, const T* rho_row,
   return rho_row[0];
 }
 
-template <typename T, bool FAST, int LAMK, bool UNIFORM, int U, bool LXF>
+template <typename T, bool FAST, int LAMK, bool UNIFORM, int U, bool LXF, bool AHEAD = false>
 __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) nonlocal_pipe_kernel(const NlArgs<T> a) {
+  static_assert(!AHEAD || UNIFORM, "publishing a tile ahead needs scalar parameters");
   constexpr int V = Vec<T>::N;
   constexpr int CPT = U * V;
   constexpr int ACC = LXF ? CPT + 2 : CPT + 1;     // look-ahead sums per thread
@@ -124,6 +127,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) nonlocal_pipe_kernel(c
       mbar_init(&sm.out_full[o], (uint32_t)(NC >> 5));
       mbar_init(&sm.out_free[o], 1);
     }
+    for (int b = 0; b < 3; ++b) mbar_init(&sm.pub[b], (uint32_t)(NC >> 5));
     fence_mbar_init();
   }
   __syncthreads();
@@ -181,35 +185,28 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) nonlocal_pipe_kernel(c
   EnvC<T> e;
   if (UNIFORM) load_uniform(e, a.u, 0, (const T*)nullptr, a.step);
 
-  int s = 0, o = 0;
-  uint32_t ph_in = 0, ph_out = 0;
-  for (int i = 0; i < n_my; ++i) {
-    const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+  auto tile_of = [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; };
+  auto active_in = [&](int tile) {
     const int envs_here = tile == last_tile ? last_envs : a.epc;
-    const int env = tile * a.epc + el;
-    const bool active = owns_cells && (el < envs_here);
-    if (active && (!UNIFORM || a.action != nullptr)) {
-      if (UNIFORM) load_uniform(e, a.u, env, a.action, a.step);
-      else load_env(e, a.table, a.flags, env, a.action, a.step);
+    return owns_cells && (el < envs_here);
+  };
+
+  // ---- first half of a tile: my cells out of input stage s, V(rho) (LXF: rho)
+  // of my cells and of the ghosts into `ve` ------------------------------------
+  auto publish_tile = [&](int s, bool active, T* ve, T (&rho)[CPT], T& rho_left) {
+    rho_left = T(0);
+    if (!active) return;
+    const uint32_t src = in0 + (uint32_t)s * NL_IN_BYTES + in_off;
+    const T* rho_row = reinterpret_cast<const T*>(sm.in[s]) + (size_t)el * N;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      T tmp[V];
+      lds16(src + 16 * u, tmp);
+#pragma unroll
+      for (int k = 0; k < V; ++k) rho[u * V + k] = tmp[k];
     }
-    T* const ve = sm.ve[i & 1];
-
-    mbar_wait(full0 + 8 * s, ph_in);
-
-    T rho[CPT];
-    T rho_left = 0;
-    if (active) {
-      const uint32_t src = in0 + (uint32_t)s * NL_IN_BYTES + in_off;
-      const T* rho_row = reinterpret_cast<const T*>(sm.in[s]) + (size_t)el * N;
+    if constexpr (!LXF) {
       T mine[CPT];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        T tmp[V];
-        lds16(src + 16 * u, tmp);
-#pragma unroll
-        for (int k = 0; k < V; ++k) rho[u * V + k] = tmp[k];
-      }
-      if constexpr (!LXF) {
       T ghost_v = T(0);   // V(rho_R) for a CONSTANT downstream end
       with_lam<LAMK>(e.flags, [&](auto kind) {
         constexpr int K = decltype(kind)::value;
@@ -231,7 +228,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) nonlocal_pipe_kernel(c
         for (int c = 0; c < n_eta; ++c) blk[(c % CPT) * VSTR + a.nthr + c / CPT] = g;
       }
       rho_left = row_first ? nl_left_ghost(a.bc, rho_row, N) : rho_row[j0 - 1];
-      } else {
+    } else {
       // LXF: the densities themselves, cell c in slot c + 1 (slot 0 = upstream
       // ghost): my cell j0 + k sits in plane (k + 1) mod CPT, column pos (+ 1
       // for my last cell)
@@ -248,13 +245,12 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) nonlocal_pipe_kernel(c
         T* blk = ve + el * (CPT * VSTR);
         for (int c = 1; c <= n_eta; ++c) blk[(c % CPT) * VSTR + a.nthr + c / CPT] = g;
       }
-      (void)mine;
-      }
     }
-    consumer_sync(NC);                               // V(rho) published; stage s read
-    if (lane0) mbar_arrive(empty0 + 8 * s);
-    mbar_wait(ofree0 + 8 * o, ph_out ^ 1);
+  };
 
+  // ---- second half: look-ahead sums, fluxes, new state into output stage o ----
+  auto finish_tile = [&](int o, bool active, int env, const T* ve, const T (&rho)[CPT],
+                         T rho_left) {
     T num = 0, den = 0;
     if (active) {
       // Godunov: W for cells j0-1 .. j0+CPT-1: acc[m] covers cell j0-1+m and
@@ -357,8 +353,74 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) nonlocal_pipe_kernel(c
         }
       }
     }
-    if (++s == NL_STAGES) { s = 0; ph_in ^= 1; }
-    if (++o == PIPE_OUT) { o = 0; ph_out ^= 1; }
+  };
+
+  if constexpr (!AHEAD) {
+    int s = 0, o = 0;
+    uint32_t ph_in = 0, ph_out = 0;
+    for (int i = 0; i < n_my; ++i) {
+      const int tile = tile_of(i);
+      const int env = tile * a.epc + el;
+      const bool active = active_in(tile);
+      if (active && (!UNIFORM || a.action != nullptr)) {
+        if (UNIFORM) load_uniform(e, a.u, env, a.action, a.step);
+        else load_env(e, a.table, a.flags, env, a.action, a.step);
+      }
+      T* const ve = sm.ve[i & 1];
+      mbar_wait(full0 + 8 * s, ph_in);
+      T rho[CPT];
+      T rho_left;
+      publish_tile(s, active, ve, rho, rho_left);
+      consumer_sync(NC);                               // V(rho) published; stage s read
+      if (lane0) mbar_arrive(empty0 + 8 * s);
+      mbar_wait(ofree0 + 8 * o, ph_out ^ 1);
+      finish_tile(o, active, env, ve, rho, rho_left);
+      if (++s == NL_STAGES) { s = 0; ph_in ^= 1; }
+      if (++o == PIPE_OUT) { o = 0; ph_out ^= 1; }
+    }
+  } else {
+    // Tile i + 1 is published BEFORE the look-ahead sums of tile i, into one of
+    // three V(rho) buffers; the CTA barrier becomes an mbarrier per buffer that
+    // is long complete by the time it is waited for (the sums take most of a
+    // tile's time), and a warp releases an input stage on its own.  A warp may
+    // write buffer (i + 1) % 3 once every warp has finished the sums of tile
+    // i - 2: that is implied by "every warp has published tile i" (a warp
+    // publishes tile i right after its sums of tile i - 2), which this warp
+    // waits for first -- it needs tile i's buffer anyway.  Scalar parameters
+    // only (two tiles' per-road constants would have to be live at once).
+    const uint32_t pub0 = smem_u32(&sm.pub[0]);
+    T rho_c[CPT], rho_n[CPT];
+    T left_c = 0, left_n = 0;
+    bool act_c = active_in(tile_of(0)), act_n = false;
+    auto fetch = [&](int i, bool active, T (&rho)[CPT], T& rho_left) {
+      const int s = i % NL_STAGES, b = i % 3;
+      mbar_wait(full0 + 8 * s, (uint32_t)((i / NL_STAGES) & 1));
+      publish_tile(s, active, sm.ve[b], rho, rho_left);
+      __syncwarp();
+      if (lane0) {
+        mbar_arrive(pub0 + 8 * b);       // my warp's part of tile i is published
+        mbar_arrive(empty0 + 8 * s);     // ... and its part of stage s is read
+      }
+    };
+    fetch(0, act_c, rho_c, left_c);
+    int o = 0;
+    uint32_t ph_out = 0;
+    for (int i = 0; i < n_my; ++i) {
+      const int tile = tile_of(i);
+      const int env = tile * a.epc + el;
+      mbar_wait(pub0 + 8 * (i % 3), (uint32_t)((i / 3) & 1));
+      if (i + 1 < n_my) {
+        act_n = active_in(tile_of(i + 1));
+        fetch(i + 1, act_n, rho_n, left_n);
+      }
+      mbar_wait(ofree0 + 8 * o, ph_out ^ 1);
+      finish_tile(o, act_c, env, sm.ve[i % 3], rho_c, left_c);
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) rho_c[k] = rho_n[k];
+      left_c = left_n;
+      act_c = act_n;
+      if (++o == PIPE_OUT) { o = 0; ph_out ^= 1; }
+    }
   }
 }
 

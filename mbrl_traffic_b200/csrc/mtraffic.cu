@@ -566,7 +566,7 @@ int pipe_vectors_per_thread() {
 
 
 // ---- non-local model launchers ------------------------------------------------
-template <typename T, bool FAST, int LAMK, bool UNIFORM, int U, bool LXF>
+template <typename T, bool FAST, int LAMK, bool UNIFORM, int U, bool LXF, bool AHEAD>
 int launch_nl_scheme(const NlArgs<T>& na, int grid, cudaStream_t stream) {
   static bool configured_dev[MAX_DEVICES] = {};
   bool* cfg_flag = configured_flag(configured_dev);
@@ -574,18 +574,35 @@ int launch_nl_scheme(const NlArgs<T>& na, int grid, cudaStream_t stream) {
   bool& configured = cfg_flag ? *cfg_flag : unused_flag;
   const size_t smem = sizeof(NlSmem<T>);
   if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(nonlocal_pipe_kernel<T, FAST, LAMK, UNIFORM, U, LXF>,
+    CUDA_TRY(cudaFuncSetAttribute(nonlocal_pipe_kernel<T, FAST, LAMK, UNIFORM, U, LXF, AHEAD>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  nonlocal_pipe_kernel<T, FAST, LAMK, UNIFORM, U, LXF><<<grid, na.nc + 32, smem, stream>>>(na);
+  nonlocal_pipe_kernel<T, FAST, LAMK, UNIFORM, U, LXF, AHEAD><<<grid, na.nc + 32, smem, stream>>>(na);
   return MT_OK;
+}
+
+// MT_NL_AHEAD=0: the non-local kernel publishes a tile and sums it in turn (A/B knob)
+bool nl_publish_ahead() {
+  static int v = -1;
+  if (v < 0) {
+    const char* s = getenv("MT_NL_AHEAD");
+    v = (s && s[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 template <typename T, bool FAST, int LAMK, bool UNIFORM, int U>
 int launch_nl(const NlArgs<T>& na, int grid, cudaStream_t stream, bool lxf = false) {
-  if (lxf) return launch_nl_scheme<T, FAST, LAMK, UNIFORM, U, true>(na, grid, stream);
-  return launch_nl_scheme<T, FAST, LAMK, UNIFORM, U, false>(na, grid, stream);
+  if constexpr (UNIFORM) {
+    // scalar parameters, no speed limits: tile i + 1 is published before tile i is summed
+    if (na.action == nullptr && nl_publish_ahead()) {
+      if (lxf) return launch_nl_scheme<T, FAST, LAMK, UNIFORM, U, true, true>(na, grid, stream);
+      return launch_nl_scheme<T, FAST, LAMK, UNIFORM, U, false, true>(na, grid, stream);
+    }
+  }
+  if (lxf) return launch_nl_scheme<T, FAST, LAMK, UNIFORM, U, true, false>(na, grid, stream);
+  return launch_nl_scheme<T, FAST, LAMK, UNIFORM, U, false, false>(na, grid, stream);
 }
 
 template <typename T, bool FAST, int U>
