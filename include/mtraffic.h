@@ -246,7 +246,7 @@ int mt_nonfinite(mt_engine *e, const void *obs, int32_t *flags_out, void *stream
  * experiments/plotting_results.ipynb cell 8): records (time, position, speed)
  * -> per (time row, section) mean speed and density.  All pointers are DEVICE
  * float64; records must be grouped by non-decreasing time row (MT_EINVAL
- * otherwise); scratch_idx holds 2*n_records int32.  Bit-equal to the
+ * otherwise); scratch_idx holds 2*n_records + 1 int32.  Bit-equal to the
  * reference's sequential accumulation.  Synchronises the stream once (to
  * read the sortedness flag). */
 int mt_aggregate(const void *time, const void *position, const void *speed,

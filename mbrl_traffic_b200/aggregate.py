@@ -35,7 +35,7 @@ def aggregate_micro(time, position, speed, dx=50.0, dt=0.5, length=1500.0,
     if m > 1 and bool((rows[1:] < rows[:-1]).any()):
         order = torch.sort(rows, stable=True).indices
         t, x, v = t[order].contiguous(), x[order].contiguous(), v[order].contiguous()
-    scratch = torch.empty(2 * max(m, 1), dtype=torch.int32, device=dev)
+    scratch = torch.empty(2 * max(m, 1) + 1, dtype=torch.int32, device=dev)
     speeds = torch.empty(n_rows, n_sections, dtype=torch.float64, device=dev)
     dens = torch.empty_like(speeds)
     stream = torch.cuda.current_stream(dev).cuda_stream

@@ -11,9 +11,15 @@
 // Determinism: the per-bin sum is taken in record order, exactly like the
 // reference's sequential loop, so the result is bit-equal to it -- no float
 // atomics.  Records must be grouped by time row in non-decreasing order (the
-// emission files are; the Python wrapper stable-sorts otherwise); one CTA owns
-// a time row, finds its record range by binary search, and each thread walks
-// that range for its sections.
+// emission files are; the Python wrapper stable-sorts otherwise).  One WARP owns
+// a time row: it finds the row's record range by binary search and walks it 32
+// records at a time; lanes whose records fall into the same section are found
+// with match.any, and the lowest of them adds the group's speeds to the
+// section's running sum in lane order -- every record is read once, every
+// section's sum is formed in record order (agg_reduce_kernel).  Rows with more
+// sections than fit the warp's shared-memory bins take the older kernel, in
+// which every thread walks the whole range for its sections
+// (agg_reduce_scan_kernel).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -69,7 +75,54 @@ __device__ __forceinline__ long long agg_lower_bound(const int* t, long long n, 
   return lo;
 }
 
+// One warp per time row; dynamic shared memory: per warp n_sections doubles
+// (sums), n_sections ints (counts), 32 doubles (the chunk's speeds).
 __global__ void agg_reduce_kernel(const AggArgs a) {
+  extern __shared__ __align__(8) unsigned char agg_smem[];
+  const int wpb = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * wpb + w;
+  const size_t per_warp = (size_t)a.n_sections * 12 + 32 * 8;
+  unsigned char* base = agg_smem + (size_t)w * ((per_warp + 7) & ~(size_t)7);
+  double* sum = reinterpret_cast<double*>(base);
+  double* chunk = sum + a.n_sections;
+  int* cnt = reinterpret_cast<int*>(chunk + 32);
+  if (row >= a.n_rows) return;
+  for (int x = lane; x < a.n_sections; x += 32) { sum[x] = 0.0; cnt[x] = 0; }
+  long long lo = 0, hi = 0;
+  if (lane == 0) {
+    lo = agg_lower_bound(a.t_idx, a.M, row);
+    hi = agg_lower_bound(a.t_idx, a.M, row + 1);
+  }
+  lo = __shfl_sync(0xffffffffu, lo, 0);
+  hi = __shfl_sync(0xffffffffu, hi, 0);
+  __syncwarp();
+  for (long long b = lo; b < hi; b += 32) {
+    const long long r = b + lane;
+    const int xi = r < hi ? a.x_idx[r] : -1;
+    chunk[lane] = r < hi ? a.speed[r] : 0.0;
+    const unsigned peers = __match_any_sync(0xffffffffu, xi);
+    __syncwarp();
+    if (xi >= 0 && lane == __ffs(peers) - 1) {      // lowest lane of the section's group
+      double s = sum[xi];
+      int c = cnt[xi];
+      for (unsigned m = peers; m != 0; m &= m - 1) {  // its records, in record order
+        s = __dadd_rn(s, chunk[__ffs(m) - 1]);
+        ++c;
+      }
+      sum[xi] = s;
+      cnt[xi] = c;
+    }
+    __syncwarp();
+  }
+  for (int x = lane; x < a.n_sections; x += 32) {
+    const size_t o = (size_t)row * a.n_sections + x;
+    const int c = cnt[x];
+    a.density_out[o] = __ddiv_rn((double)c, a.dx);
+    a.speed_out[o] = c == 0 ? a.empty_speed : __ddiv_rn(sum[x], (double)c);
+  }
+}
+
+__global__ void agg_reduce_scan_kernel(const AggArgs a) {
   const int row = blockIdx.x;
   __shared__ long long s_lo, s_hi;
   if (threadIdx.x == 0) {

@@ -1636,8 +1636,8 @@ int mt_aggregate(const void* time, const void* position, const void* speed, int6
     return fail(MT_EINVAL, "mt_aggregate: bad shape or step");
   CUDA_TRY(cudaSetDevice(device));
   cudaStream_t s = (cudaStream_t)stream;
-  int* flag = nullptr;
-  CUDA_TRY(cudaMalloc((void**)&flag, sizeof(int)));
+  // the "rows out of order" flag is the scratch buffer's last word (no allocation here)
+  int* flag = (int*)scratch_idx + 2 * n_records;
   cudaError_t err = cudaMemsetAsync(flag, 0, sizeof(int), s);
   AggArgs a;
   a.time = (const double*)time; a.pos = (const double*)position; a.speed = (const double*)speed;
@@ -1653,14 +1653,20 @@ int mt_aggregate(const void* time, const void* position, const void* speed, int6
     agg_index_kernel<<<grid, block, 0, s>>>(a);
     agg_check_sorted_kernel<<<grid, block, 0, s>>>(a);
   }
+  // (the error contract needs the flag on the host: one 4-byte copy and a wait)
   if (err == cudaSuccess)
     err = cudaMemcpyAsync(&unsorted, flag, sizeof(int), cudaMemcpyDeviceToHost, s);
   if (err == cudaSuccess) err = cudaStreamSynchronize(s);
   if (err == cudaSuccess && !unsorted) {
-    agg_reduce_kernel<<<(unsigned)n_rows, 128, 0, s>>>(a);
+    const size_t per_warp = (((size_t)n_sections * 12 + 32 * 8) + 7) & ~(size_t)7;
+    int wpb = 4;
+    while (wpb > 1 && per_warp * wpb > 48 * 1024) wpb >>= 1;
+    if (per_warp * wpb <= 48 * 1024)
+      agg_reduce_kernel<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, per_warp * wpb, s>>>(a);
+    else
+      agg_reduce_scan_kernel<<<(unsigned)n_rows, 128, 0, s>>>(a);
     err = cudaGetLastError();
   }
-  cudaFree(flag);
   if (err != cudaSuccess) return fail(MT_ECUDA, "mt_aggregate: %s", cudaGetErrorString(err));
   if (unsorted) return fail(MT_EINVAL, "mt_aggregate: records must be grouped by non-decreasing time row");
   return MT_OK;
