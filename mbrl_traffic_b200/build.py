@@ -24,6 +24,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
     "-Xcompiler", "-fPIC",
+    # kernels of one translation unit are launched from another (extern template)
+    "-static-global-template-stub=false",
     "-I", os.path.join(ROOT, "include"),
 ]
 # No `-split-compile`: it halves the build time of the big translation unit but
