@@ -48,7 +48,8 @@
 extern "C" {
 #endif
 
-#define MT_VERSION 100 /* 0.1.0 */
+#define MT_VERSION 200 /* 0.2.0: mt_params grew (scheme, alpha), mt_aggregate's scratch
+                          * holds one more word, new entry points (see below)       */
 
 typedef struct mt_engine mt_engine;
 

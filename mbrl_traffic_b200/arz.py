@@ -24,8 +24,12 @@ class ARZModel(FiniteVolumeModel):
     (arz.py:199): assigning ``rho_max`` later does not move it.
 
     Extra keyword arguments (not in the reference): ``device``,
-    ``action_is_speed_limit``, ``fast_math``.  ``rho_max``, ``v_max``, ``tau``
-    and ``lam`` may also be arrays with one value per row of a batched ``obs``.
+    ``action_is_speed_limit``, ``fast_math``, ``fsolve_abort`` (mimic the
+    reference on roads with an exact-zero density, where its fsolve call gives
+    up and the relative flow stays frozen for the road, arz.py:411, 460-463;
+    off by default: the closed form gives NaN at the affected cells only).
+    ``rho_max``, ``v_max``, ``tau`` and ``lam`` may also be arrays with one
+    value per row of a batched ``obs``.
     """
 
     _engine_model = "arz"
