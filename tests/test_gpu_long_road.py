@@ -120,6 +120,8 @@ def test_exchange_folded_into_the_step_launches_emulated(kind, dtype, world, hal
     the whole road, cell for cell, also after a period shorter than the halo
     and when the run is continued by the separate pull / step path."""
     _need_gpu()
+    if os.environ.get("MT_NO_FUSE") == "1":
+        pytest.skip("MT_NO_FUSE=1 switches the several-steps-per-launch kernel off")
     from mbrl_traffic_b200.engine import Engine
     name = np.dtype(dtype).name
     periods, tail = 4, 3
@@ -177,6 +179,8 @@ def test_exchange_folded_into_the_step_launches_emulated(kind, dtype, world, hal
 
 def test_halo_advance_argument_checks():
     _need_gpu()
+    if os.environ.get("MT_NO_FUSE") == "1":
+        pytest.skip("MT_NO_FUSE=1 switches the several-steps-per-launch kernel off")
     from mbrl_traffic_b200 import _lib
     from mbrl_traffic_b200.dist import PeerHalo
     from mbrl_traffic_b200.engine import Engine
