@@ -187,6 +187,10 @@ __global__ void actor_head_kernel(const __nv_bfloat16* __restrict__ h,
                                   const __nv_bfloat16* __restrict__ w,
                                   const __nv_bfloat16* __restrict__ bias, T* __restrict__ action,
                                   long long B, int H, float scale) {
+  // the step kernel enqueued next (a programmatic dependent launch) may set up
+  // its pipeline while this kernel runs; it reads the actions only after its
+  // own grid-dependency wait, i.e. after this kernel has completed
+  pdl_launch_dependents();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= B) return;
   const int lane = threadIdx.x & 31;
