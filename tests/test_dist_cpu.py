@@ -153,3 +153,18 @@ def test_advance_runs_whole_blocks_and_refreshes():
     assert blocks == [4, 4, 3]
     d2.advance(out, 2)                # finishes the open block first: 1 + 1
     assert blocks == [4, 4, 3, 1, 1]
+
+
+def test_begin_starts_a_new_run_on_the_same_object():
+    """begin() == scatter() plus a reset of the exchange state (without a
+    mailbox there is no pending push to consume)."""
+    n, halo = 120, 4
+    road = _make_road(n, seed=11)
+    base = _oracle_stepper("arz", "extend_both")
+    d = DomainDecomposedRoad(n, 0, 1, halo, base, exchange=lambda a, b: (None, None))
+    first = d.advance(d.begin(road), 6)
+    assert d._since_exchange == 2
+    again = d.advance(d.begin(road), 6)
+    assert d._since_exchange == 2
+    assert np.array_equal(first, again)
+    assert np.array_equal(d.begin(road), d.scatter(road))

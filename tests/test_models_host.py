@@ -205,3 +205,32 @@ def test_header_is_plain_c_and_links_against_the_library(tmp_path):
     out = subprocess.run([str(exe)], stdout=subprocess.PIPE, universal_newlines=True, check=True)
     version, cfg_size, handle = out.stdout.split()
     assert int(version) > 0 and int(cfg_size) == 40 and int(handle) == 64
+
+
+def test_nonlocal_scheme_choice_and_schema(tmp_path):
+    """scheme / alpha (round 2): validated at construction, kept by save / load,
+    and the Lax-Friedrichs CFL number uses the viscosity."""
+    from mbrl_traffic_b200 import NonLocalModel, NONLOCAL_MODEL_PARAMS
+    with pytest.raises(ValueError, match="Unknown scheme"):
+        NonLocalModel(scheme="upwind", **_params(NONLOCAL_MODEL_PARAMS))
+    m = NonLocalModel(scheme="lxf", alpha=35.0, **_params(NONLOCAL_MODEL_PARAMS))
+    assert m.scheme == "lxf" and m.alpha == 35.0
+    g0 = float(m.weights()[0])
+    assert abs(m.cfl_number() - 0.5 / 50 * (35.0 + g0 * 30)) < 1e-15
+    assert m._engine_kwargs()["scheme"] == "lxf"
+    m.save(str(tmp_path))
+    m2 = NonLocalModel(**_params(NONLOCAL_MODEL_PARAMS))
+    assert m2.scheme == "godunov" and m2.alpha is None
+    m2.load(str(tmp_path / "model.json"))
+    assert m2.scheme == "lxf" and m2.alpha == 35.0
+
+
+def test_abi_flags_and_version():
+    assert _lib.MT_FLAG_DEPENDENT_INPUT == 8 and _lib.MT_FLAG_FSOLVE_ABORT == 16
+    assert (_lib.MT_SCHEME_GODUNOV, _lib.MT_SCHEME_LXF) == (0, 1)
+    with open(os.path.join(ROOT, "include", "mtraffic.h")) as f:
+        header = f.read()
+    for name in ("MT_FLAG_DEPENDENT_INPUT = 8", "MT_FLAG_FSOLVE_ABORT = 16", "MT_SCHEME_LXF = 1",
+                 "#define MT_VERSION 200"):
+        assert name in header, name
+    assert _lib.load().mt_version() == 200
