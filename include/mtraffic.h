@@ -207,11 +207,15 @@ int mt_step_obs16(mt_engine *e, const void *obs_in, const void *action,
  * envs/vsl.py:92-100):  action[b] = scale * (tanh(hidden[b,:] . weight + bias)
  * + 1), hidden (B, n_hidden) / weight (n_hidden) / bias (1) bfloat16 DEVICE
  * arrays, action in `dtype` (mt_dtype) -- the buffer mt_step reads its speed
- * limits from.  Asynchronous on stream. */
+ * limits from.  reward_prev / return_sum (both or neither; DEVICE [B] in
+ * `dtype`): return_sum[b] += reward_prev[b], the accumulation of a rollout's
+ * return (algorithm.py:564-620 sums rewards per episode) riding on this launch
+ * -- pass the reward buffer of the PREVIOUS step.  Asynchronous on stream. */
 int mt_actor_head(int32_t device, int32_t dtype, const void *hidden_bf16,
                   const void *weight_bf16, const void *bias_bf16,
                   void *action_out, int64_t n_envs, int32_t n_hidden,
-                  double scale, void *stream);
+                  double scale, const void *reward_prev, void *return_sum,
+                  void *stream);
 
 /* n_steps chained steps ping-ponging between two caller-owned DEVICE batches,
  * starting from obs_a.  actions: DEVICE [n_steps, B] or NULL.  rewards:

@@ -99,7 +99,7 @@ def load():
     lib.mt_step_obs16.restype = ctypes.c_int
     lib.mt_step_obs16.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.mt_actor_head.restype = ctypes.c_int
-    lib.mt_actor_head.argtypes = [i32, i32, vp, vp, vp, vp, i64, i32, ctypes.c_double, vp]
+    lib.mt_actor_head.argtypes = [i32, i32, vp, vp, vp, vp, i64, i32, ctypes.c_double, vp, vp, vp]
     lib.mt_rollout.restype = ctypes.c_int
     lib.mt_rollout.argtypes = [vp, vp, vp, vp, vp, i32, vp,
                                ctypes.POINTER(i32)]

@@ -186,7 +186,8 @@ template <typename T>
 __global__ void actor_head_kernel(const __nv_bfloat16* __restrict__ h,
                                   const __nv_bfloat16* __restrict__ w,
                                   const __nv_bfloat16* __restrict__ bias, T* __restrict__ action,
-                                  long long B, int H, float scale) {
+                                  long long B, int H, float scale,
+                                  const T* __restrict__ reward_prev, T* __restrict__ return_sum) {
   // the step kernel enqueued next (a programmatic dependent launch) may set up
   // its pipeline while this kernel runs; it reads the actions only after its
   // own grid-dependency wait, i.e. after this kernel has completed
@@ -202,6 +203,9 @@ __global__ void actor_head_kernel(const __nv_bfloat16* __restrict__ h,
     // the reference layer rounds its output to the activation dtype before tanh
     const float z = __bfloat162float(__float2bfloat16_rn(acc + __bfloat162float(bias[0])));
     action[row] = (T)(scale * (tanhf(z) + 1.0f));
+    // the rollout's return accumulates here: the previous step's reward (already
+    // final: that step kernel completed before this kernel started) joins the sum
+    if (return_sum != nullptr) return_sum[row] += reward_prev[row];
   }
 }
 
@@ -1412,11 +1416,13 @@ int mt_step_obs16(mt_engine* e, const void* obs_in, const void* action, void* ob
 
 int mt_actor_head(int32_t device, int32_t dtype, const void* hidden_bf16, const void* weight_bf16,
                   const void* bias_bf16, void* action_out, int64_t n_envs, int32_t n_hidden,
-                  double scale, void* stream) {
+                  double scale, const void* reward_prev, void* return_sum, void* stream) {
   if (!hidden_bf16 || !weight_bf16 || !bias_bf16 || !action_out)
     return fail(MT_EINVAL, "mt_actor_head: NULL argument");
   if (n_envs < 0 || n_hidden < 1) return fail(MT_EINVAL, "mt_actor_head: bad sizes");
   if (dtype != MT_F32 && dtype != MT_F64) return fail(MT_EINVAL, "mt_actor_head: unknown dtype");
+  if ((reward_prev == nullptr) != (return_sum == nullptr))
+    return fail(MT_EINVAL, "mt_actor_head: reward_prev and return_sum go together");
   CUDA_TRY(cudaSetDevice(device));
   if (n_envs == 0) return MT_OK;
   const int wpb = 8;
@@ -1426,11 +1432,13 @@ int mt_actor_head(int32_t device, int32_t dtype, const void* hidden_bf16, const 
   if (dtype == MT_F64)
     actor_head_kernel<double><<<(unsigned)grid, wpb * 32, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)hidden_bf16, (const __nv_bfloat16*)weight_bf16,
-        (const __nv_bfloat16*)bias_bf16, (double*)action_out, n_envs, n_hidden, (float)scale);
+        (const __nv_bfloat16*)bias_bf16, (double*)action_out, n_envs, n_hidden, (float)scale,
+        (const double*)reward_prev, (double*)return_sum);
   else
     actor_head_kernel<float><<<(unsigned)grid, wpb * 32, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)hidden_bf16, (const __nv_bfloat16*)weight_bf16,
-        (const __nv_bfloat16*)bias_bf16, (float*)action_out, n_envs, n_hidden, (float)scale);
+        (const __nv_bfloat16*)bias_bf16, (float*)action_out, n_envs, n_hidden, (float)scale,
+        (const float*)reward_prev, (float*)return_sum);
   CUDA_TRY(cudaGetLastError());
   return MT_OK;
 }

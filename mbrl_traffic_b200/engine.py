@@ -226,12 +226,15 @@ class Engine(object):
         return out.value
 
 
-def actor_head(hidden, weight, bias, action_out, scale, stream=None):
+def actor_head(hidden, weight, bias, action_out, scale, stream=None, reward_prev=None,
+               return_sum=None):
     """``mt_actor_head``: ``action_out[b] = scale * (tanh(hidden[b] . weight +
     bias) + 1)`` -- the output layer of a speed-limit policy written straight
     into the engine-dtype buffer ``mt_step`` reads its actions from.  ``hidden``
     (B, H), ``weight`` (H,) / (1, H), ``bias`` (1,): contiguous bfloat16 device
-    tensors; ``action_out``: (B,) float32 / float64 device tensor."""
+    tensors; ``action_out``: (B,) float32 / float64 device tensor.  With
+    ``reward_prev`` / ``return_sum`` (both (B,) in the dtype of ``action_out``)
+    the launch also does ``return_sum += reward_prev``."""
     lib = _lib.load()
     b, h = hidden.shape
     if weight.numel() != h or bias.numel() != 1 or action_out.numel() != b:
@@ -239,7 +242,7 @@ def actor_head(hidden, weight, bias, action_out, scale, stream=None):
     _lib.check(lib.mt_actor_head(
         hidden.device.index or 0, _DTYPES[dtype_name(action_out.dtype)], _ptr(hidden),
         _ptr(weight), _ptr(bias), _ptr(action_out), int(b), int(h), float(scale),
-        _stream_ptr(stream)))
+        _ptr(reward_prev), _ptr(return_sum), _stream_ptr(stream)))
     return action_out
 
 

@@ -106,7 +106,7 @@ class FeedForwardActor(nn.Module):
         x = self.net(obs.to(self.net[0].weight.dtype))
         return (0.5 * self.v_max_max) * (torch.tanh(x.squeeze(-1)) + 1.0)
 
-    def act_bf16(self, obs16, action_out):
+    def act_bf16(self, obs16, action_out, reward_prev=None, return_sum=None):
         """The same policy for a bfloat16 network and a bfloat16 observation
         (``BatchedMacroEnv(obs_bf16=True).obs16``), written into
         ``action_out`` (``(B,)`` in the engine dtype): hidden layers as GEMMs
@@ -119,7 +119,8 @@ class FeedForwardActor(nn.Module):
         for lin in linears[:-1]:
             x = torch._addmm_activation(lin.bias, x, lin.weight.t())   # relu(x W^T + b)
         last = linears[-1]
-        return actor_head(x, last.weight, last.bias, action_out, 0.5 * self.v_max_max)
+        return actor_head(x, last.weight, last.bias, action_out, 0.5 * self.v_max_max,
+                          reward_prev=reward_prev, return_sum=return_sum)
 
 
 class PolicyRollout(object):
@@ -145,11 +146,16 @@ class PolicyRollout(object):
         env = self.env
         with torch.no_grad():
             if self.fused:
-                act = self.actor.act_bf16(env.obs16, self.action)
+                # the return accumulates on the output layer's launch: it adds the
+                # PREVIOUS step's reward (zero before the first step; the last
+                # step's reward is added by run())
+                act = self.actor.act_bf16(env.obs16, self.action, reward_prev=env.reward,
+                                          return_sum=self.total)
             else:
                 act = self.actor(env.obs).to(env.dtype).contiguous()
         _, r, _, _ = env.step(act)
-        self.total.add_(r)
+        if not self.fused:
+            self.total.add_(r)
 
     def _capture(self):
         env = self.env
@@ -176,12 +182,16 @@ class PolicyRollout(object):
         with torch.cuda.stream(self.stream):
             env.reset(obs0)
             self.total.zero_()
+            if self.fused:
+                env.reward.zero_()
             done = 0
             while done + 2 <= horizon:
                 self.graph.replay()
                 done += 2
             for _ in range(horizon - done):
                 self._one()
+            if self.fused:
+                self.total.add_(env.reward)        # the last step's reward
         torch.cuda.current_stream(env.device).wait_stream(self.stream)
         return self.total
 
