@@ -177,7 +177,11 @@ const char *mt_last_error(void);
 int mt_create(const mt_config *cfg, mt_engine **out);
 void mt_destroy(mt_engine *e);
 
-/* Derive the per-env constant table on the device (asynchronous on stream). */
+/* Derive the per-env constant table on the device (asynchronous on stream).
+ * With per-road arrays the call then waits for that kernel and reads 8 bytes
+ * back (do all roads share an exponent kind? is every rho_max 1?) to pick a
+ * step kernel without the run-time dispatch; not while the stream is being
+ * captured, where the general kernel is kept. */
 int mt_set_params(mt_engine *e, const mt_params *p, void *stream);
 
 /* One step for the whole batch.  obs_in/obs_out: DEVICE (B, 2N).  action:

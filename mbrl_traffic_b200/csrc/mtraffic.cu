@@ -78,6 +78,7 @@ template <typename T> struct ParamArgs {
   int pow_fast;  // MT_FLAG_FAST_MATH
   double rho_max, v_max, tau, lam, rho_crit, dt;
   const T *rho_max_env, *v_max_env, *tau_env, *lam_env, *rho_crit_env;
+  unsigned* summary;   // [0] |= 1 << exponent kind of every road, [1] |= (rho_max != 1)
 };
 
 template <typename T>
@@ -122,6 +123,13 @@ __global__ void set_params_kernel(const ParamArgs<T> p) {
   row[TBL_FLAGS] = (T)fl;
   for (int k = TBL_FLAGS + 1; k < TBL_STRIDE; ++k) row[k] = T(0);
   p.flags[env] = fl;
+  // batch-wide summary (one atomic per warp and word)
+  const unsigned kinds = __reduce_or_sync(__activemask(), 1u << fl);
+  const unsigned not_one = __reduce_or_sync(__activemask(), rho_max != T(1) ? 1u : 0u);
+  if ((threadIdx.x & 31) == 0) {
+    atomicOr(p.summary, kinds);
+    if (not_one) atomicOr(p.summary + 1, 1u);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -231,6 +239,10 @@ struct mt_engine {
   // UNIFORM kernel instantiations (host arithmetic == device arithmetic)
   bool uniform = false;
   int lamk = LAM_RUNTIME;
+  // per-road tables: the exponent kind ALL roads share (LAM_ONE_RM1 when they
+  // also all have rho_max == 1), or LAM_RUNTIME; read back by mt_set_params
+  int table_lamk = LAM_RUNTIME;
+  unsigned* summary = nullptr;   // device, 2 words
   UniformC<double> u64;
   UniformC<float> u32;
   int64_t launches = 0;
@@ -485,12 +497,22 @@ int launch_pipe(const PipeArgs<T>& pa, int grid, cudaStream_t stream) {
 }
 
 template <typename T, int MODEL, bool FAST, int U>
-int launch_pipe_lam(const PipeArgs<T>& pa, int grid, bool uniform, int lamk, cudaStream_t s) {
+int launch_pipe_lam(const PipeArgs<T>& pa, int grid, bool uniform, int lamk, cudaStream_t s,
+                    int table_lamk = LAM_RUNTIME) {
   if (uniform && lamk == LAM_ONE && pa.u.rho_max == T(1))
     return launch_pipe<T, MODEL, FAST, LAM_ONE_RM1, true, U>(pa, grid, s);
   if (uniform && lamk == LAM_ONE) return launch_pipe<T, MODEL, FAST, LAM_ONE, true, U>(pa, grid, s);
   if (uniform && lamk == LAM_TWO) return launch_pipe<T, MODEL, FAST, LAM_TWO, true, U>(pa, grid, s);
   if (uniform && lamk == LAM_HALF) return launch_pipe<T, MODEL, FAST, LAM_HALF, true, U>(pa, grid, s);
+  // per-road tables whose roads all share an exponent kind (ARZ f64: the
+  // instantiations exist in mt_pipe_arz64.cu)
+  if constexpr (MODEL == 1 && sizeof(T) == 8 && !FAST) {
+    if (!uniform && table_lamk == LAM_ONE_RM1)
+      return launch_pipe<T, MODEL, FAST, LAM_ONE_RM1, false, U>(pa, grid, s);
+    if (!uniform && table_lamk == LAM_ONE) return launch_pipe<T, MODEL, FAST, LAM_ONE, false, U>(pa, grid, s);
+    if (!uniform && table_lamk == LAM_TWO) return launch_pipe<T, MODEL, FAST, LAM_TWO, false, U>(pa, grid, s);
+    if (!uniform && table_lamk == LAM_HALF) return launch_pipe<T, MODEL, FAST, LAM_HALF, false, U>(pa, grid, s);
+  }
   return launch_pipe<T, MODEL, FAST, LAM_RUNTIME, false, U>(pa, grid, s);
 }
 
@@ -499,11 +521,11 @@ template <> struct FastAllowed<float> { static constexpr bool value = true; };
 
 template <typename T, int MODEL, int U>
 int launch_pipe_model(const PipeArgs<T>& pa, int grid, bool fast, bool uniform, int lamk,
-                      cudaStream_t s) {
+                      cudaStream_t s, int table_lamk = LAM_RUNTIME) {
   if constexpr (FastAllowed<T>::value) {
     if (fast) return launch_pipe_lam<T, MODEL, true, U>(pa, grid, uniform, lamk, s);
   }
-  return launch_pipe_lam<T, MODEL, false, U>(pa, grid, uniform, lamk, s);
+  return launch_pipe_lam<T, MODEL, false, U>(pa, grid, uniform, lamk, s, table_lamk);
 }
 
 template <typename T> const UniformC<T>& uniform_of(const mt_engine* e);
@@ -1033,8 +1055,8 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
     mine.out_hi = mine.out_lo + (size_t)B * 2 * N * sizeof(T);
     int rc;
     if (e->cfg.model == MT_MODEL_ARZ)
-      rc = U == 2 ? launch_pipe_model<T, 1, 2>(pa, grid, fast, e->uniform, e->lamk, stream)
-                  : launch_pipe_model<T, 1, 1>(pa, grid, fast, e->uniform, e->lamk, stream);
+      rc = U == 2 ? launch_pipe_model<T, 1, 2>(pa, grid, fast, e->uniform, e->lamk, stream, e->table_lamk)
+                  : launch_pipe_model<T, 1, 1>(pa, grid, fast, e->uniform, e->lamk, stream, e->table_lamk);
     else
       rc = U == 2 ? launch_pipe_model<T, 0, 2>(pa, grid, fast, e->uniform, e->lamk, stream)
                   : launch_pipe_model<T, 0, 1>(pa, grid, fast, e->uniform, e->lamk, stream);
@@ -1284,6 +1306,7 @@ int mt_create(const mt_config* cfg, mt_engine** out) {
   e->max_tiles = g.tiles;
   cudaError_t err = cudaMalloc(&e->table, B * TBL_STRIDE * e->elt);
   if (err == cudaSuccess) err = cudaMalloc((void**)&e->flags, B * sizeof(int));
+  if (err == cudaSuccess) err = cudaMalloc((void**)&e->summary, 2 * sizeof(unsigned));
   if (err == cudaSuccess && g.tiles > 1) err = cudaMalloc(&e->partial, B * g.tiles * 2 * e->elt);
   const size_t sched_bytes = 2 * (1 + mt_engine::HOST_STREAMS) * sizeof(unsigned int);
   if (err == cudaSuccess) err = cudaMalloc((void**)&e->sched, sched_bytes);
@@ -1318,6 +1341,7 @@ void mt_destroy(mt_engine* e) {
   cudaSetDevice(e->cfg.device);
   cudaFree(e->table);
   cudaFree(e->flags);
+  cudaFree(e->summary);
   cudaFree(e->partial);
   cudaFree(e->sched);
   cudaFree(e->d_a);
@@ -1355,13 +1379,14 @@ int mt_set_params(mt_engine* e, const mt_params* p, void* stream) {
   const int block = 128;
   const unsigned grid = (unsigned)((B + block - 1) / block);
   cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(e->summary, 0, 2 * sizeof(unsigned), s));
   if (e->cfg.dtype == MT_F64) {
     ParamArgs<double> a{(double*)e->table, e->flags, B, e->cfg.model,
                         (p->flags & MT_FLAG_FAST_MATH) ? 1 : 0, p->rho_max, p->v_max,
                         p->tau, p->lam, p->rho_crit, p->dt,
                         (const double*)p->rho_max_env, (const double*)p->v_max_env,
                         (const double*)p->tau_env, (const double*)p->lam_env,
-                        (const double*)p->rho_crit_env};
+                        (const double*)p->rho_crit_env, e->summary};
     set_params_kernel<double><<<grid, block, 0, s>>>(a);
   } else {
     ParamArgs<float> a{(float*)e->table, e->flags, B, e->cfg.model,
@@ -1369,7 +1394,7 @@ int mt_set_params(mt_engine* e, const mt_params* p, void* stream) {
                        p->tau, p->lam, p->rho_crit, p->dt,
                        (const float*)p->rho_max_env, (const float*)p->v_max_env,
                        (const float*)p->tau_env, (const float*)p->lam_env,
-                       (const float*)p->rho_crit_env};
+                       (const float*)p->rho_crit_env, e->summary};
     set_params_kernel<float><<<grid, block, 0, s>>>(a);
   }
   note_forget(e->cfg.device, s);
@@ -1387,6 +1412,22 @@ int mt_set_params(mt_engine* e, const mt_params* p, void* stream) {
     else make_uniform<float>(e->u32, lamk, e->cfg.model, *p);
     e->lamk = lamk;
     if (lamk == LAM_GENERAL) e->uniform = false;  // pow(): use the device table
+  }
+  // Per-road arrays: which exponent kind do ALL roads share?  One 8-byte
+  // readback (and a wait for the kernel above) buys a step kernel without the
+  // run-time dispatch -- and, when every rho_max is 1, without the division
+  // rho / rho_max.  Not during stream capture (no waiting there): such engines
+  // keep the general kernel.
+  e->table_lamk = LAM_RUNTIME;
+  const bool arrays = p->rho_max_env || p->v_max_env || p->tau_env || p->lam_env || p->rho_crit_env;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (arrays && cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
+    unsigned host[2] = {0u, 0u};
+    CUDA_TRY(cudaMemcpyAsync(host, e->summary, sizeof(host), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (host[0] == (1u << LAM_ONE)) e->table_lamk = host[1] ? LAM_ONE : LAM_ONE_RM1;
+    else if (host[0] == (1u << LAM_TWO)) e->table_lamk = LAM_TWO;
+    else if (host[0] == (1u << LAM_HALF)) e->table_lamk = LAM_HALF;
   }
   return MT_OK;
 }
