@@ -504,9 +504,9 @@ int launch_pipe_lam(const PipeArgs<T>& pa, int grid, bool uniform, int lamk, cud
   if (uniform && lamk == LAM_ONE) return launch_pipe<T, MODEL, FAST, LAM_ONE, true, U>(pa, grid, s);
   if (uniform && lamk == LAM_TWO) return launch_pipe<T, MODEL, FAST, LAM_TWO, true, U>(pa, grid, s);
   if (uniform && lamk == LAM_HALF) return launch_pipe<T, MODEL, FAST, LAM_HALF, true, U>(pa, grid, s);
-  // per-road tables whose roads all share an exponent kind (ARZ f64: the
-  // instantiations exist in mt_pipe_arz64.cu)
-  if constexpr (MODEL == 1 && sizeof(T) == 8 && !FAST) {
+  // per-road tables whose roads all share an exponent kind (f64; the ARZ
+  // instantiations live in mt_pipe_arz64.cu)
+  if constexpr (sizeof(T) == 8 && !FAST) {
     if (!uniform && table_lamk == LAM_ONE_RM1)
       return launch_pipe<T, MODEL, FAST, LAM_ONE_RM1, false, U>(pa, grid, s);
     if (!uniform && table_lamk == LAM_ONE) return launch_pipe<T, MODEL, FAST, LAM_ONE, false, U>(pa, grid, s);
@@ -1058,8 +1058,8 @@ int step_typed(mt_engine* e, const void* obs_in_, const void* action_, void* obs
       rc = U == 2 ? launch_pipe_model<T, 1, 2>(pa, grid, fast, e->uniform, e->lamk, stream, e->table_lamk)
                   : launch_pipe_model<T, 1, 1>(pa, grid, fast, e->uniform, e->lamk, stream, e->table_lamk);
     else
-      rc = U == 2 ? launch_pipe_model<T, 0, 2>(pa, grid, fast, e->uniform, e->lamk, stream)
-                  : launch_pipe_model<T, 0, 1>(pa, grid, fast, e->uniform, e->lamk, stream);
+      rc = U == 2 ? launch_pipe_model<T, 0, 2>(pa, grid, fast, e->uniform, e->lamk, stream, e->table_lamk)
+                  : launch_pipe_model<T, 0, 1>(pa, grid, fast, e->uniform, e->lamk, stream, e->table_lamk);
     if (rc != MT_OK) return rc;
     e->launches++;
     CUDA_TRY(cudaGetLastError());

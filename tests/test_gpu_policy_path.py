@@ -108,3 +108,45 @@ def test_fused_policy_rollout_graph_equals_eager_and_tracks_the_plain_path():
         a_fused = actor.act_bf16(obs.to(torch.bfloat16), act).float()
     assert float((a_plain - a_fused).abs().max()) < 0.5     # of a [0, 30] range, bf16 layers
     model.close()
+
+
+@pytest.mark.parametrize("case", ["rm1", "one", "two", "half", "mixed"])
+@pytest.mark.parametrize("b,n", [(300, 1000), (37, 250)])
+def test_per_road_tables_with_a_shared_exponent_kind(case, b, n):
+    """mt_set_params reads back whether all roads share an exponent kind (and
+    whether every rho_max is 1) and the step then runs with the kind as a
+    compile-time constant; every variant -- and the general kernel for mixed
+    kinds -- is bit-equal to the oracle, single step, with rewards, and as a
+    fused rollout."""
+    _need_gpu()
+    from mbrl_traffic_b200.engine import Engine
+    from oracle import np_oracle as o
+    rng = np.random.default_rng(len(case) * 1000 + n)
+    lam = {"rm1": np.ones(b), "one": np.ones(b), "two": np.full(b, 2.0), "half": np.full(b, 0.5),
+           "mixed": rng.choice([1.0, 2.0, 0.5], b)}[case]
+    rho_max = np.ones(b) if case == "rm1" else rng.choice([1.0, 0.5, 0.2], b)
+    v_max = rng.uniform(15, 30, b)
+    tau = rng.uniform(5, 20, b)
+    rho = rho_max[:, None] * rng.uniform(0.05, 0.9, (b, n))
+    v = v_max[:, None] * (1 - rho / rho_max[:, None]) ** lam[:, None] + rng.normal(0, 1, (b, n))
+    obs = np.concatenate((rho, v), axis=1)
+    dev = "cuda:0"
+    eng = Engine("arz", "float64", b, n)
+    eng.set_params(dx=50, dt=0.5, rho_max=torch.as_tensor(rho_max, device=dev),
+                   v_max=torch.as_tensor(v_max, device=dev), lam=torch.as_tensor(lam, device=dev),
+                   tau=torch.as_tensor(tau, device=dev), boundary_conditions="loop")
+    kw = dict(dx=50, dt=0.5, rho_max=rho_max, v_max=v_max, lam=lam, tau=tau,
+              rho_crit=rho_max / 2, boundary_conditions="loop")
+    x = torch.as_tensor(obs, device=dev)
+    y = torch.empty_like(x)
+    rew = torch.empty(b, dtype=torch.float64, device=dev)
+    eng.step(x, y, reward=rew)
+    ref = o.arz_step(obs, **kw)
+    assert np.array_equal(y.cpu().numpy(), ref)
+    np.testing.assert_allclose(rew.cpu().numpy(), o.mean_speed_reward(ref), rtol=1e-12)
+    ref4 = obs
+    for _ in range(4):
+        ref4 = o.arz_step(ref4, **kw)
+    out4 = eng.rollout(x.clone(), y, 4)
+    assert np.array_equal(out4.cpu().numpy(), ref4)
+    eng.close()
