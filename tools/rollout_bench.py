@@ -22,7 +22,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mbrl_traffic_b200 import ARZModel, ARZ_MODEL_PARAMS  # noqa: E402
 from mbrl_traffic_b200.rollout import (BatchedMacroEnv, FeedForwardActor,  # noqa: E402
-                                       KShootPolicy, policy_rollout)
+                                       KShootPolicy, PolicyRollout, policy_rollout)
 
 
 def main():
@@ -58,7 +58,8 @@ def main():
     rho = rng.uniform(0.05, 0.9, (b, n))
     v = 30 * (1 - rho) + rng.normal(0, 1, (b, n))
     obs = torch.as_tensor(np.concatenate((rho, v), 1), device="cuda").to(tdt)
-    env = BatchedMacroEnv(model, b, n, horizon=args.horizon, dtype=tdt)
+    env = BatchedMacroEnv(model, b, n, horizon=args.horizon, dtype=tdt,
+                          obs_bf16=(args.actor_dtype == "bfloat16"))
     # A random-init actor is an erratic controller: some seeds command speed
     # limits near zero and back within a few steps, which drives the reference
     # scheme itself unstable (negative densities, overflow -- the NumPy oracle
@@ -66,11 +67,15 @@ def main():
     torch.manual_seed(1)
     actor = FeedForwardActor(2 * n).to("cuda").to(getattr(torch, args.actor_dtype))
     out = {}
+    runner = PolicyRollout(env, actor)       # captured once, replayed for every rollout
     for graph in (False, True):
-        policy_rollout(env, actor, obs, horizon=8, use_graph=graph)
+        if graph:
+            runner.run(obs, horizon=8)
+        else:
+            policy_rollout(env, actor, obs, horizon=8, use_graph=False)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        total = policy_rollout(env, actor, obs, use_graph=graph)
+        total = runner.run(obs) if graph else policy_rollout(env, actor, obs, use_graph=False)
         torch.cuda.synchronize()
         dt = slowest(time.perf_counter() - t0)
         out["graph" if graph else "eager"] = dict(
