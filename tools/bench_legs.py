@@ -112,27 +112,35 @@ def leg_nonlocal(ctx, args):
     gamma = torch.as_tensor(gamma_np, device=ctx.dev)
     bc = {"inflow_outflow": 0.3}
     eng = Engine("nonlocal", "float64", b, n, device=ctx.local_rank, max_n_eta=256)
-    eng.set_params(dx=dx, dt=dt, rho_max=1, v_max=30, lam=1, boundary_conditions=bc,
-                   gamma=gamma)
     sets = 2
     ins = [torch.as_tensor(make_obs(b, n, 100 + ctx.rank * sets + j), device=ctx.dev)
            for j in range(sets)]
     outs = [torch.empty_like(x) for x in ins]
     stream = torch.cuda.Stream(device=ctx.dev)
     steps = args.nonlocal_steps
-    with torch.cuda.stream(stream):
-        for k in range(4):
-            eng.step(ins[k % sets], outs[k % sets], stream=stream)
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=stream):
-            for k in range(steps):
+
+    def measure(scheme):
+        eng.set_params(dx=dx, dt=dt, rho_max=1, v_max=30, lam=1, boundary_conditions=bc,
+                       gamma=gamma, scheme=scheme)
+        with torch.cuda.stream(stream):
+            for k in range(4):
                 eng.step(ins[k % sets], outs[k % sets], stream=stream)
-    graph.replay()
-    torch.cuda.synchronize()
-    sec, times = timed_replays(ctx, graph, 5, stream)
-    # (parity of this kernel: tests/test_gpu_parity.py::test_nonlocal_*)
-    finite = ctx.all_ok(bool(torch.isfinite(outs[0]).all().item()))
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream):
+                for k in range(steps):
+                    eng.step(ins[k % sets], outs[k % sets], stream=stream)
+        graph.replay()
+        torch.cuda.synchronize()
+        sec_, _ = timed_replays(ctx, graph, 5, stream)
+        ok = ctx.all_ok(bool(torch.isfinite(outs[0]).all().item()))
+        return sec_, ok
+
+    # the second scheme (Lax-Friedrichs, mean downstream density) rides along
+    sec_lxf, finite_lxf = measure("lxf")
+    sec, finite = measure("godunov")
+    # (parity of these kernels: tests/test_gpu_parity.py::test_nonlocal_*,
+    #  tests/test_nonlocal_unpinned.py)
     cells = b * n
     per_step = sec / steps
     gbs = cells * 24 / per_step / 1e9
@@ -145,6 +153,11 @@ def leg_nonlocal(ctx, args):
               "algorithmic_bytes_per_cell_update": 24,
               "roofline_frac": gbs / ctx.peak, "achieved_GBps": gbs,
               "scaling": "weak", "outputs_finite": finite,
+              "lxf": {"value": ctx.world * cells / (sec_lxf / steps), "unit": "cell-updates/s",
+                      "roofline_frac": cells * 24 / (sec_lxf / steps) / 1e9 / ctx.peak,
+                      "outputs_finite": finite_lxf,
+                      "what": "the same batch under scheme=\"lxf\" (Blandin-Goatin model, "
+                              "Lax-Friedrichs flux)"},
               "parity_note": "parity unpinned: no reference implementation exists; the oracle "
                              "restates the cited paper (tests/test_gpu_parity.py::test_nonlocal_*)",
               "l2": "2 independent batches round-robin, %.0f MB working set per GPU"
