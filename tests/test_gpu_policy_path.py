@@ -150,3 +150,30 @@ def test_per_road_tables_with_a_shared_exponent_kind(case, b, n):
     out4 = eng.rollout(x.clone(), y, 4)
     assert np.array_equal(out4.cpu().numpy(), ref4)
     eng.close()
+
+
+def test_population_loss_with_general_exponents_stays_within_the_promise():
+    """float64 population scoring evaluates x**lam with the engine's own
+    exp2(lam log2 x) (5e-15 relative): every candidate's loss equals the
+    oracle's (NumPy pow) to 1e-12, far inside the 1e-13-per-cell promise for
+    exponents outside {1, 2, 0.5}."""
+    _need_gpu()
+    from mbrl_traffic_b200 import ARZModel, ARZ_MODEL_PARAMS
+    from oracle import np_oracle as o
+    b, n, p = 64, 30, 16
+    rng = np.random.default_rng(71)
+    rho = 0.2 * rng.uniform(0.05, 0.9, (b, n))
+    obs = np.concatenate((rho, 30 * (1 - rho / 0.2) + rng.normal(0, 1, (b, n))), axis=1)
+    rho2 = 0.2 * rng.uniform(0.05, 0.9, (b, n))
+    nxt = np.concatenate((rho2, 30 * (1 - rho2 / 0.2) + rng.normal(0, 1, (b, n))), axis=1)
+    params = dict(ARZ_MODEL_PARAMS)
+    params.pop("optimizer_cls")
+    m = ARZModel(None, None, None, None, 0, optimizer_cls=None, **params)
+    cand = np.column_stack([rng.uniform(0.55, 1.0, p), rng.uniform(5, 30, p),
+                            rng.uniform(1, 25, p), rng.uniform(0.6, 3.5, p)])
+    losses = m.population_loss(cand, obs, None, nxt)
+    for i in range(p):
+        ref = o.density_mse(nxt, o.arz_step(obs, rho_max=cand[i, 0], v_max=cand[i, 1],
+                                            tau=cand[i, 2], lam=cand[i, 3], rho_crit=0.5))
+        assert abs(losses[i] - ref) <= 1e-12 * abs(ref), (i, losses[i], ref)
+    m.close()
