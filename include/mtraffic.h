@@ -162,7 +162,9 @@ typedef struct mt_params {
   int32_t bc_left, bc_right;  /* mt_bc                                       */
   double bc_left_val[2];      /* CONSTANT: rho (LWR, non-local) or (rho, y)  */
   double bc_right_val[2];     /*           for ARZ (arz.py:347-360)          */
-  const void *gamma;          /* non-local: DEVICE array of n_eta weights    */
+  const void *gamma;          /* non-local: DEVICE array of n_eta weights;
+                                 the sums take them in ascending k, one
+                                 fused multiply-add per term             */
   int32_t n_eta;
   int32_t flags;
   int32_t scheme;             /* non-local: mt_scheme                        */

@@ -8,8 +8,13 @@
 //     F_{j+1/2} = rho_j W_j
 //     rho'_j    = rho_j - (dt/dx) (F_{j+1/2} - F_{j-1/2}),   v'_j = V(rho'_j)
 //
-// exactly as oracle/np_oracle.py nonlocal_step evaluates it (same operation
-// order, no FMA in EXACT mode).
+// exactly as oracle/np_oracle.py nonlocal_step evaluates it: same operation
+// order; the look-ahead sum accumulates with ONE fused multiply-add per term
+// (w = fma(gamma_k, V, w)) -- no reference code exists for this model, so the
+// rounding of that sum is ours to define, and the fused form is both the more
+// accurate one and half the FP64 instructions of the kernel's inner loop (the
+// oracle emulates it exactly, np_oracle.fma).  Everything else is separately
+// rounded as in the LWR / ARZ kernels.
 //
 // Second scheme (LXF = true; mt_params.scheme = MT_SCHEME_LXF): the model of
 // Blandin & Goatin, Numer. Math. 132 (2016), whose speed depends on a mean of
@@ -271,7 +276,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) nonlocal_pipe_kernel(c
         const int x = k + ACC;
         const T nxt = vcol[(x % CPT) * VSTR + x / CPT];
 #pragma unroll
-        for (int m = 0; m < ACC; ++m) acc[m] = A::mad(g, win[m], acc[m]);  // w + gamma_k * V
+        for (int m = 0; m < ACC; ++m) acc[m] = A::fma(g, win[m], acc[m]);  // fma(gamma_k, V, w)
 #pragma unroll
         for (int m = 0; m < ACC - 1; ++m) win[m] = win[m + 1];
         win[ACC - 1] = nxt;
@@ -470,7 +475,7 @@ __global__ void nonlocal_lxf_scalar_kernel(const NlScalarArgs<T> a) {
   for (int k = 0; k < a.n_eta; ++k) {
     const T g = a.gamma[k];
 #pragma unroll
-    for (int m = 0; m < 3; ++m) r[m] = A::mad(g, nl_rho_at(a.bc, row, N, j - 1 + m + k), r[m]);
+    for (int m = 0; m < 3; ++m) r[m] = A::fma(g, nl_rho_at(a.bc, row, N, j - 1 + m + k), r[m]);
   }
   T c[3], gq[3];
 #pragma unroll
@@ -502,8 +507,8 @@ __global__ void nonlocal_scalar_kernel(const NlScalarArgs<T> a) {
   T w = T(0), wm = T(0);
   for (int k = 0; k < a.n_eta; ++k) {
     const T g = a.gamma[k];
-    w = A::mad(g, v_eq<T, FAST, LAMK>(nl_rho_at(a.bc, row, N, j + k + 1), e), w);
-    wm = A::mad(g, v_eq<T, FAST, LAMK>(nl_rho_at(a.bc, row, N, j + k), e), wm);
+    w = A::fma(g, v_eq<T, FAST, LAMK>(nl_rho_at(a.bc, row, N, j + k + 1), e), w);
+    wm = A::fma(g, v_eq<T, FAST, LAMK>(nl_rho_at(a.bc, row, N, j + k), e), wm);
   }
   const T rho = row[j];
   const T F = A::mul(rho, w);

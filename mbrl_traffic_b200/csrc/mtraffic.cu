@@ -668,7 +668,9 @@ int step_nonlocal(mt_engine* e, const T* obs_in, const T* action, T* obs_out, T*
   const T half_alpha = p.alpha < 0 ? T(-1) : (T)(0.5 * p.alpha);
   if (n_eta > N) return fail(MT_EINVAL, "non-local: n_eta (%d) exceeds n_cells (%d)", n_eta, N);
   int U = pipe_vectors_per_thread();
-  if (U == 0) U = (sizeof(T) == 8) ? 2 : 1;
+  // two 16-byte pieces per thread in both types: fewer window reads and look-ahead
+  // sums per cell (float32, 16384 x 1000, n_eta 16: 0.54 -> 0.64 of the copy roofline)
+  if (U == 0) U = 2;
   if (N % (U * V) != 0 || N < 2 * U * V) U = 1;
   const int CPT = U * V;
   bool pipe_ok = aligned && (N % CPT == 0) && (N >= 2 * CPT) && !(p.flags & MT_FLAG_NO_PIPELINE) &&

@@ -9,6 +9,11 @@ their speed to a weighted mean of the downstream equilibrium speeds over a
 look-ahead distance ``eta``.  ``scheme="lxf"`` selects the other classical
 variant instead: the speed of a weighted mean of the downstream DENSITIES with
 a Lax-Friedrichs flux (Blandin & Goatin, Numer. Math. 132, 2016).
+
+Rounding (there is no reference code to follow): the look-ahead sums take
+their terms in ascending k, each joined by ONE fused multiply-add,
+``w = fma(gamma_k, V, w)``; everything else is separately rounded like the
+LWR / ARZ steps.  ``oracle/np_oracle.py`` evaluates exactly that.
 """
 import json
 import os

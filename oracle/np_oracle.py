@@ -263,6 +263,45 @@ def arz_step(obs, dx=50, dt=0.5, rho_max=1, v_max=30, tau=9, lam=1,
 # Non-local look-ahead model -- no reference code; parity unpinned            #
 # --------------------------------------------------------------------------- #
 
+def _two_sum(x, y):
+    s = x + y
+    bb = s - x
+    return s, (x - (s - bb)) + (y - bb)
+
+
+def _veltkamp(a):
+    c = 134217729.0 * a          # 2**27 + 1
+    hi = c - (c - a)
+    return hi, a - hi
+
+
+def fma(a, b, c):
+    """Correctly rounded ``a * b + c`` (one rounding), element-wise, float64.
+
+    NumPy has no fused multiply-add; this is the classic error-free route:
+    Dekker's exact product ``p + e = a * b`` (Veltkamp splitting), ``s + t = p +
+    c`` exactly (Knuth's TwoSum), the small terms ``t + e`` rounded TO ODD, and
+    one final round-to-nearest addition (Boldo & Melquiond, "Emulation of FMA and
+    correctly rounded sums", IEEE TC 2008).  Valid away from overflow and
+    underflow, which is where the traffic models live; checked against the C
+    library's ``fma`` in tests/test_nonlocal_unpinned.py.  float32 inputs are
+    evaluated in float64 and rounded once more (the non-local float32 tests are
+    tolerance tests)."""
+    out_dtype = np.result_type(a, b, c)
+    a, b, c = np.broadcast_arrays(np.asarray(a, np.float64), np.asarray(b, np.float64),
+                                  np.asarray(c, np.float64))
+    p = a * b
+    ah, al = _veltkamp(a)
+    bh, bl = _veltkamp(b)
+    e = ((ah * bh - p) + ah * bl + al * bh) + al * bl
+    s, t = _two_sum(p, c)
+    u, r = _two_sum(t, e)
+    even = (np.ascontiguousarray(u).view(np.int64) & 1) == 0
+    v = np.where((r != 0) & even, np.nextafter(u, np.where(r > 0, np.inf, -np.inf)), u)
+    res = s + v
+    return res.astype(out_dtype) if out_dtype == np.float32 else res
+
+
 def nonlocal_weights(eta, dx, kernel="linear", dtype=np.float64):
     """Cell weights gamma_k = int_{k dx}^{(k+1) dx} w_eta(y) dy, k < n_eta.
 
@@ -317,7 +356,9 @@ def nonlocal_step(obs, gamma, dx=50, dt=0.5, rho_max=1, v_max=30, lam=1,
     Scheme (2.4)-(2.5) of Friedrich, Kolb, Goettlich, NHM 13 (2018) with
     g(rho) = rho:
 
-        W_j     = sum_{k=0}^{n_eta-1} gamma_k V(rho_{j+k+1})   (k ascending)
+        W_j     = sum_{k=0}^{n_eta-1} gamma_k V(rho_{j+k+1})   (k ascending,
+                  each term joined by a fused multiply-add: w = fma(gamma_k, V, w)
+                  -- one rounding per term; no reference code fixes the order)
         F_{j+1/2} = rho_j W_j
         rho'_j  = rho_j - (dt/dx) (F_{j+1/2} - F_{j-1/2})
 
@@ -334,7 +375,7 @@ def nonlocal_step(obs, gamma, dx=50, dt=0.5, rho_max=1, v_max=30, lam=1,
     # W for cells -1 .. N-1  (ext index j+1 <-> cell j)
     w = np.zeros((rho.shape[0], n + 1), dtype=rho.dtype)
     for k in range(n_eta):
-        w = w + gamma[k] * ve[:, k + 1:k + 1 + n + 1]
+        w = fma(gamma[k], ve[:, k + 1:k + 1 + n + 1], w)
     flux = ext[:, :n + 1] * w            # F_{j+1/2} for j = -1 .. N-1
     rho_tp1 = rho - step * (flux[:, 1:] - flux[:, :-1])
     v_tp1 = v_eq(rho_tp1, v_max, rho_max, lam)
@@ -349,7 +390,8 @@ def nonlocal_lxf_step(obs, gamma, dx=50, dt=0.5, rho_max=1, v_max=30, lam=1,
     (2016), scheme (3.2)-(3.4); the second scheme BASELINE.json's north_star
     names).  PARITY UNPINNED: the reference holds no code for it.
 
-        R_j       = sum_{k=0}^{n_eta-1} gamma_k rho_{j+k}        (k ascending)
+        R_j       = sum_{k=0}^{n_eta-1} gamma_k rho_{j+k}        (k ascending, fused
+                    multiply-adds as in nonlocal_step)
         g_j       = rho_j V(R_j)
         F_{j+1/2} = 0.5 (g_j + g_{j+1}) + (0.5 alpha) (rho_j - rho_{j+1})
         rho'_j    = rho_j - (dt/dx) (F_{j+1/2} - F_{j-1/2})
@@ -370,7 +412,7 @@ def nonlocal_lxf_step(obs, gamma, dx=50, dt=0.5, rho_max=1, v_max=30, lam=1,
     # R for cells -1 .. N  (ext index c+1 <-> cell c)
     r = np.zeros((rho.shape[0], n + 2), dtype=rho.dtype)
     for k in range(n_eta):
-        r = r + gamma[k] * ext[:, k:k + n + 2]
+        r = fma(gamma[k], ext[:, k:k + n + 2], r)
     cells = ext[:, :n + 2]
     g = cells * v_eq(r, v_max, rho_max, lam)
     half_alpha = 0.5 * _col(v_max if alpha is None else alpha, rho.dtype)

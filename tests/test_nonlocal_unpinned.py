@@ -13,10 +13,18 @@ reference vectors here:
   model: the two schemes must approach each other under refinement;
 * the CUDA kernels (pipelined and scalar) against the oracle, bit for bit.
 """
+from fractions import Fraction
+
 import numpy as np
 import pytest
 
 from oracle import np_oracle as o
+
+
+def _fma(a, b, c):
+    """Exact fused multiply-add through rational arithmetic (float() of a
+    Fraction rounds to nearest even)."""
+    return float(Fraction(a) * Fraction(b) + Fraction(c))
 
 BCS = ["loop", "extend_both", {"constant_both": (0.3, 0.2)}, {"inflow_outflow": 0.3}]
 
@@ -59,7 +67,7 @@ def scalar_nonlocal(row, gamma, dx, dt, rho_max, v_max, lam, bc, scheme):
             for c in (j - 1, j):                    # F_{c+1/2} = rho_c W_c
                 w = 0.0
                 for k, g in enumerate(gamma):
-                    w = w + g * _v(_rho_at(row, c + k + 1, bc), v_max, rho_max, lam)
+                    w = _fma(g, _v(_rho_at(row, c + k + 1, bc), v_max, rho_max, lam), w)
                 face.append(_rho_at(row, c, bc) * w)
             out[j] = row[j] - step * (face[1] - face[0])
         else:
@@ -67,7 +75,7 @@ def scalar_nonlocal(row, gamma, dx, dt, rho_max, v_max, lam, bc, scheme):
             for c in (j - 1, j, j + 1):
                 r = 0.0
                 for k, g in enumerate(gamma):
-                    r = r + g * _rho_at(row, c + k, bc)
+                    r = _fma(g, _rho_at(row, c + k, bc), r)
                 cell.append(_rho_at(row, c, bc))
                 gq.append(cell[-1] * _v(r, v_max, rho_max, lam))
             ha = 0.5 * v_max
@@ -102,6 +110,28 @@ def test_oracle_equals_independent_scalar_restatement_parity_unpinned(scheme, bc
     for i in range(b):
         ref = scalar_nonlocal(rho[i], g, 50, 0.5, rho_max, 25.0, lam, bc, scheme)
         assert np.array_equal(got[i], ref), (scheme, bci, i)
+
+
+def test_oracle_fma_equals_the_c_library_fma():
+    """np_oracle.fma (error-free product + round-to-odd) against libm's fma on
+    random and adversarial operands (near-cancellation, long mantissas)."""
+    import ctypes
+    import ctypes.util
+    libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    libm.fma.restype = ctypes.c_double
+    libm.fma.argtypes = [ctypes.c_double] * 3
+    rng = np.random.default_rng(0)
+    n = 20000
+    a = np.concatenate([rng.uniform(0, 0.2, n), rng.uniform(-1, 1, n),
+                        1 + rng.integers(0, 2 ** 20, n) * 2.0 ** -52])
+    b = np.concatenate([rng.uniform(0, 30, n), rng.uniform(-1, 1, n),
+                        1 + rng.integers(0, 2 ** 20, n) * 2.0 ** -52])
+    c = np.concatenate([rng.uniform(0, 30, n), -rng.uniform(-1, 1, n) * rng.uniform(-1, 1, n),
+                        -(1 + rng.integers(0, 2 ** 21, n) * 2.0 ** -52)])
+    got = o.fma(a, b, c)
+    ref = np.array([libm.fma(x, y, z) for x, y, z in zip(a.tolist(), b.tolist(), c.tolist())])
+    assert np.array_equal(got, ref)
+    assert _fma(0.1, 0.2, -0.02) == libm.fma(0.1, 0.2, -0.02)
 
 
 def test_lookahead_weights_have_unit_mass_and_do_not_increase():
