@@ -50,7 +50,15 @@
 
 namespace mt {
 
-constexpr int NL_STAGES = 4;
+// CTAs per SM.  3: 72 registers per thread (no spills), two input stages, two
+// V(rho) buffers, tiles published and summed in turn (no AHEAD): 27 warps per
+// SM instead of 18 for a kernel bound by the latency of its FP64 chains.
+#ifndef MT_NL_CTAS
+#define MT_NL_CTAS 2
+#endif
+constexpr int NL_CTAS = MT_NL_CTAS;
+constexpr int NL_STAGES = NL_CTAS >= 3 ? 2 : 4;
+constexpr int NL_VE_BUFS = NL_CTAS >= 3 ? 2 : 3;
 constexpr int NL_IN_BYTES = PIPE_TILE_BYTES / 2;   // densities of one tile (8 KB)
 constexpr int NL_MAX_ETA = 256;                    // look-ahead cells
 constexpr int NL_GHOSTS = 320;                     // extra V(rho) slots per tile for ghosts
@@ -59,7 +67,7 @@ template <typename T> struct NlSmem {
   static constexpr int VE = NL_IN_BYTES / (int)sizeof(T) + NL_GHOSTS + 64;
   alignas(128) unsigned char in[NL_STAGES][NL_IN_BYTES];
   alignas(128) unsigned char out[PIPE_OUT][PIPE_TILE_BYTES];
-  alignas(16) T ve[3][VE];          // V(rho) of the tile incl. ghosts: two buffers in turn, or
+  alignas(16) T ve[NL_VE_BUFS][VE];        // V(rho) of the tile incl. ghosts: two buffers in turn, or
                                     // three when tiles are published one ahead (AHEAD)
   T gamma[NL_MAX_ETA];
   T s_num[PIPE_BLOCK / 32], s_den[PIPE_BLOCK / 32];
@@ -69,7 +77,8 @@ template <typename T> struct NlSmem {
   uint64_t out_free[PIPE_OUT];
   uint64_t pub[3];                  // AHEAD: every consumer warp has published buffer b
 };
-static_assert(sizeof(NlSmem<double>) <= 113 * 1024, "two CTAs per SM must fit in 227 KB");
+static_assert(sizeof(NlSmem<double>) <= (NL_CTAS >= 3 ? 75 : 113) * 1024,
+              "NL_CTAS CTAs per SM must fit in 227 KB (1 KB reserved per CTA)");
 
 template <typename T> struct NlArgs {
   const T* in;
@@ -98,8 +107,9 @@ __device__ __forceinline__ T nl_left_ghost(const BcArgs<T>& b, const T* rho_row,
 }
 
 template <typename T, bool FAST, int LAMK, bool UNIFORM, int U, bool LXF, bool AHEAD = false>
-__global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) nonlocal_pipe_kernel(const NlArgs<T> a) {
+__global__ void __launch_bounds__(PIPE_BLOCK / U + 32, NL_CTAS) nonlocal_pipe_kernel(const NlArgs<T> a) {
   static_assert(!AHEAD || UNIFORM, "publishing a tile ahead needs scalar parameters");
+  if constexpr (AHEAD && NL_VE_BUFS < 3) return;   // never launched in that build
   constexpr int V = Vec<T>::N;
   constexpr int CPT = U * V;
   constexpr int ACC = LXF ? CPT + 2 : CPT + 1;     // look-ahead sums per thread
@@ -398,7 +408,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) nonlocal_pipe_kernel(c
     T left_c = 0, left_n = 0;
     bool act_c = active_in(tile_of(0)), act_n = false;
     auto fetch = [&](int i, bool active, T (&rho)[CPT], T& rho_left) {
-      const int s = i % NL_STAGES, b = i % 3;
+      const int s = i % NL_STAGES, b = i % 3 % NL_VE_BUFS;   // (AHEAD needs three buffers)
       mbar_wait(full0 + 8 * s, (uint32_t)((i / NL_STAGES) & 1));
       publish_tile(s, active, sm.ve[b], rho, rho_left);
       __syncwarp();
@@ -419,7 +429,7 @@ __global__ void __launch_bounds__(PIPE_BLOCK / U + 32, 2) nonlocal_pipe_kernel(c
         fetch(i + 1, act_n, rho_n, left_n);
       }
       mbar_wait(ofree0 + 8 * o, ph_out ^ 1);
-      finish_tile(o, act_c, env, sm.ve[i % 3], rho_c, left_c);
+      finish_tile(o, act_c, env, sm.ve[i % 3 % NL_VE_BUFS], rho_c, left_c);
 #pragma unroll
       for (int k = 0; k < CPT; ++k) rho_c[k] = rho_n[k];
       left_c = left_n;

@@ -617,7 +617,7 @@ bool nl_publish_ahead() {
   static int v = -1;
   if (v < 0) {
     const char* s = getenv("MT_NL_AHEAD");
-    v = (s && s[0] == '0') ? 0 : 1;
+    v = (s && s[0] == '0') || NL_VE_BUFS < 3 ? 0 : 1;
   }
   return v != 0;
 }
@@ -698,7 +698,7 @@ int step_nonlocal(mt_engine* e, const T* obs_in, const T* action, T* obs_out, T*
     na.n_tiles = (int)((B + na.epc - 1) / na.epc);
     na.bc = bc; na.step = step; na.u = uniform_of<T>(e);
     na.half_alpha = half_alpha;
-    const long long slots = 2LL * e->sm_count;
+    const long long slots = (long long)NL_CTAS * e->sm_count;
     const int grid = (int)(na.n_tiles < slots ? na.n_tiles : slots);
     const int rc = U == 2 ? launch_nl_fast<T, 2>(na, grid, fast, e->uniform, e->lamk, stream, lxf)
                           : launch_nl_fast<T, 1>(na, grid, fast, e->uniform, e->lamk, stream, lxf);
